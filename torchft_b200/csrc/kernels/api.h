@@ -1,0 +1,55 @@
+// Host-callable launchers of the torchft_b200 data-plane kernels.
+// Raw pointers + cudaStream_t only: no torch headers anywhere in this extension.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace tft {
+
+struct PeerTable;
+struct StatusBlock;
+
+// allreduce.cu ---------------------------------------------------------------
+// algo: 0 = one-shot, 1 = two-shot. op: 0 sum, 1 max, 2 min. Consumes barrier
+// values flag+1 and flag+2 on `channel`.
+void allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* user_in,
+                      void* user_out, size_t nelem, int dtype, int op, float scale,
+                      uint64_t flag, int channel, int contribute, int algo, int blocks,
+                      int threads, cudaStream_t stream);
+
+// quant.cu -------------------------------------------------------------------
+size_t q8_ngroups(size_t nelem, int world);
+size_t q8_buffer_bytes(size_t nelem, int world);
+void q8_quantize_launch(const void* a, const void* b, size_t nelem, int dtype, int world,
+                        void* qbuf, cudaStream_t stream);
+void q8_dequantize_launch(const void* qbuf, size_t nelem, int dtype, int world, void* out,
+                          cudaStream_t stream);
+void q8_reduce_launch(const void* const* srcs_dev, int world, int rank, size_t nelem,
+                      float post_scale, void* dst, cudaStream_t stream);
+void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* in_a,
+                         const void* in_b, void* out, size_t nelem, int dtype, float post_scale,
+                         uint64_t flag, int channel, int contribute, int blocks,
+                         cudaStream_t stream);
+
+// model_ops.cu ---------------------------------------------------------------
+void rmsnorm_fwd_launch(const void* x, const void* w, void* y, float* rstd, int rows, int H,
+                        float eps, cudaStream_t s);
+int rmsnorm_bwd_grid(int rows);
+void rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                        float* dw_partial, void* dw, int accumulate, int rows, int H,
+                        cudaStream_t s);
+void swiglu_fwd_launch(const void* gu, void* y, size_t T, int F, cudaStream_t s);
+void swiglu_bwd_launch(const void* dy, const void* gu, void* dgu, size_t T, int F, cudaStream_t s);
+void rope_launch(const void* in, void* out, const void* cs, size_t T, int S, int heads, int D,
+                 size_t in_stride, size_t out_stride, float sign, cudaStream_t s);
+void xent_launch(void* logits, const void* target, float* loss, size_t rows, int V,
+                 size_t row_stride, float grad_scale, long long ignore_index, cudaStream_t s);
+void adamw_launch(void* p, float* master, float* m, float* v, const void* g, size_t n, float lr,
+                  float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
+                  const int* gate, cudaStream_t s);
+void sumsq_launch(const void* g, size_t n, float* out, cudaStream_t s);
+void heal_copy_launch(const void* table_dev, int nentries, size_t total_chunks, size_t chunk_bytes,
+                      int blocks, cudaStream_t s);
+
+}  // namespace tft

@@ -1,0 +1,492 @@
+// Fused bandwidth-bound model ops for the Llama training step (sm_100a):
+// RMSNorm fwd/bwd, SwiGLU fwd/bwd, RoPE, softmax-cross-entropy fwd+bwd,
+// flat AdamW with fp32 master weights and a device-side commit gate.
+//
+// The reference (torchft) ships no model; its flagship config (BASELINE.json:
+// Llama-3-8B HSDP) gets these from eager PyTorch/torchtitan. Here every
+// elementwise/normalisation/activation step is one pass over HBM with 16 B
+// accesses; GEMMs stay on cuBLAS and attention on the SDPA library kernel.
+// All activations are bf16, all reductions fp32.
+#include <stdexcept>
+#include <string>
+
+#include "api.h"
+#include "common.cuh"
+
+namespace tft {
+
+using bf16 = __nv_bfloat16;
+using P8 = Pack<bf16>;
+
+// ------------------------------- RMSNorm ------------------------------------
+// One CTA per row, row cached in registers (H <= 8 * 4 * blockDim).
+constexpr int kRmsMaxVec = 4;
+
+template <int NV>
+__global__ void __launch_bounds__(512) rmsnorm_fwd_kernel(const bf16* __restrict__ x,
+                                                          const bf16* __restrict__ w,
+                                                          bf16* __restrict__ y,
+                                                          float* __restrict__ rstd, int rows, int H,
+                                                          float eps) {
+  __shared__ float red[32];
+  const int nvec = H / 8;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const bf16* xr = x + (size_t)row * H;
+    float f[NV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        P8::unpack(ld_stream(xr + v * 8), f[i]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ss += f[i][k] * f[i][k];
+      }
+    }
+    ss = block_sum(ss, red);
+    const float r = rsqrtf(ss / H + eps);
+    if (threadIdx.x == 0) rstd[row] = r;
+    bf16* yr = y + (size_t)row * H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        float wf[8], o[8];
+        P8::unpack(*reinterpret_cast<const Vec16*>(w + v * 8), wf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = f[i][k] * r * wf[k];
+        st_stream(yr + v * 8, P8::pack(o));
+      }
+    }
+  }
+}
+
+// dx = rstd * (dy*w - xhat * mean(dy*w*xhat)); dw_partial[block] += dy * xhat
+template <int NV>
+__global__ void __launch_bounds__(512) rmsnorm_bwd_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+    const float* __restrict__ rstd, bf16* __restrict__ dx, float* __restrict__ dw_partial,
+    int rows, int H) {
+  __shared__ float red[32];
+  const int nvec = H / 8;
+  float dw[NV][8];
+  float wf[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dw[i][k] = 0.f;
+    if (v < nvec) P8::unpack(*reinterpret_cast<const Vec16*>(w + v * 8), wf[i]);
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float r = rstd[row];
+    float xh[NV][8], g[NV][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        float xf[8], dyf[8];
+        P8::unpack(ld_stream(x + (size_t)row * H + v * 8), xf);
+        P8::unpack(ld_stream(dy + (size_t)row * H + v * 8), dyf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          xh[i][k] = xf[k] * r;
+          g[i][k] = dyf[k] * wf[i][k];
+          dot += g[i][k] * xh[i][k];
+          dw[i][k] += dyf[k] * xh[i][k];
+        }
+      }
+    }
+    dot = block_sum(dot, red) / H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = r * (g[i][k] - xh[i][k] * dot);
+        st_stream(dx + (size_t)row * H + v * 8, P8::pack(o));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float* o = dw_partial + (size_t)blockIdx.x * H + v * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(dw[i][4], dw[i][5], dw[i][6], dw[i][7]);
+    }
+  }
+}
+
+// dw[h] (+)= sum_b partial[b][h]
+__global__ void colsum_kernel(const float* __restrict__ partial, int nb, int H,
+                              bf16* __restrict__ dw, int accumulate) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partial[(size_t)b * H + h];
+  if (accumulate) s += __bfloat162float(dw[h]);
+  dw[h] = __float2bfloat16(s);
+}
+
+// ------------------------------- SwiGLU -------------------------------------
+// gu: [T, 2F] (gate | up), y: [T, F]
+__global__ void __launch_bounds__(512) swiglu_fwd_kernel(const bf16* __restrict__ gu,
+                                                         bf16* __restrict__ y, size_t T, int F) {
+  const size_t nvec_row = F / 8;
+  const size_t total = T * nvec_row;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i / nvec_row, c = (i % nvec_row) * 8;
+    float g[8], u[8], o[8];
+    P8::unpack(ld_stream(gu + t * 2 * F + c), g);
+    P8::unpack(ld_stream(gu + t * 2 * F + F + c), u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = g[k] / (1.f + __expf(-g[k])) * u[k];
+    st_stream(y + t * F + c, P8::pack(o));
+  }
+}
+
+__global__ void __launch_bounds__(512) swiglu_bwd_kernel(const bf16* __restrict__ dy,
+                                                         const bf16* __restrict__ gu,
+                                                         bf16* __restrict__ dgu, size_t T, int F) {
+  const size_t nvec_row = F / 8;
+  const size_t total = T * nvec_row;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i / nvec_row, c = (i % nvec_row) * 8;
+    float g[8], u[8], d[8], dg[8], du[8];
+    P8::unpack(ld_stream(gu + t * 2 * F + c), g);
+    P8::unpack(ld_stream(gu + t * 2 * F + F + c), u);
+    P8::unpack(ld_stream(dy + t * F + c), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float s = 1.f / (1.f + __expf(-g[k]));
+      const float silu = g[k] * s;
+      du[k] = d[k] * silu;
+      dg[k] = d[k] * u[k] * (s + silu * (1.f - s));
+    }
+    st_stream(dgu + t * 2 * F + c, P8::pack(dg));
+    st_stream(dgu + t * 2 * F + F + c, P8::pack(du));
+  }
+}
+
+// ------------------------------- RoPE ---------------------------------------
+// Interleaved-pair rotation (x[2i], x[2i+1]) by angle pos * theta_i; cs holds
+// (cos, sin) pairs: cs[pos][i] = float2. sign = +1 forward, -1 backward.
+// in/out row strides in elements so q/k can be read straight out of the packed
+// qkv projection and written contiguous.
+__global__ void __launch_bounds__(256) rope_kernel(const bf16* __restrict__ in,
+                                                   bf16* __restrict__ out,
+                                                   const float2* __restrict__ cs, size_t T, int S,
+                                                   int heads, int D, size_t in_stride,
+                                                   size_t out_stride, float sign) {
+  const int vec_per_head = D / 8;
+  const size_t total = T * heads * vec_per_head;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int vh = i % vec_per_head;
+    const size_t th = i / vec_per_head;
+    const int h = th % heads;
+    const size_t t = th / heads;
+    const int pos = t % S;
+    float f[8], o[8];
+    P8::unpack(ld_stream(in + t * in_stride + (size_t)h * D + vh * 8), f);
+    const float2* c = cs + (size_t)pos * (D / 2) + vh * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 v = c[k];
+      const float sn = v.y * sign;
+      o[2 * k] = f[2 * k] * v.x - f[2 * k + 1] * sn;
+      o[2 * k + 1] = f[2 * k] * sn + f[2 * k + 1] * v.x;
+    }
+    st_stream(out + t * out_stride + (size_t)h * D + vh * 8, P8::pack(o));
+  }
+}
+
+// ------------------------------- Cross entropy ------------------------------
+// One CTA per row of logits [rows, V] (bf16). Writes loss[row] (fp32) and
+// overwrites the logits row with d(loss_sum * grad_scale)/dlogits in bf16.
+// Rows whose target == ignore_index get loss 0 and zero gradient.
+__global__ void __launch_bounds__(1024) xent_fwd_bwd_kernel(bf16* __restrict__ logits,
+                                                            const long long* __restrict__ target,
+                                                            float* __restrict__ loss, int V,
+                                                            size_t row_stride, float grad_scale,
+                                                            long long ignore_index) {
+  __shared__ float red[32];
+  const size_t row = blockIdx.x;
+  bf16* lr = logits + row * row_stride;
+  const long long tgt = target[row];
+  const int nvec = V / 8;
+  if (tgt == ignore_index) {
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) st_stream(lr + v * 8, Vec16{0, 0, 0, 0});
+    for (int k = nvec * 8 + threadIdx.x; k < V; k += blockDim.x) lr[k] = __float2bfloat16(0.f);
+    if (threadIdx.x == 0) loss[row] = 0.f;
+    return;
+  }
+  // pass 1: online max / sum-exp
+  float m = -INFINITY, s = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float f[8];
+    P8::unpack(*reinterpret_cast<const Vec16*>(lr + v * 8), f);
+    float lm = f[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) lm = fmaxf(lm, f[k]);
+    const float nm = fmaxf(m, lm);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += __expf(f[k] - nm);
+    s = s * __expf(m - nm) + acc;
+    m = nm;
+  }
+  for (int k = nvec * 8 + threadIdx.x; k < V; k += blockDim.x) {
+    const float x = __bfloat162float(lr[k]);
+    const float nm = fmaxf(m, x);
+    s = s * __expf(m - nm) + __expf(x - nm);
+    m = nm;
+  }
+  const float gm = block_max(m, red);
+  s = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
+  const float gs = block_sum(s, red);
+  const float lse = gm + __logf(gs);
+  if (threadIdx.x == 0) loss[row] = lse - __bfloat162float(lr[tgt]);
+  __syncthreads();  // everyone done reading lr[tgt] region before overwrite
+  const float inv = grad_scale / gs;
+  // pass 2: grad = (softmax - onehot) * grad_scale   (row is L2-resident)
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float f[8], o[8];
+    P8::unpack(*reinterpret_cast<const Vec16*>(lr + v * 8), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o[k] = __expf(f[k] - gm) * inv;
+      if ((long long)v * 8 + k == tgt) o[k] -= grad_scale;
+    }
+    st_stream(lr + v * 8, P8::pack(o));
+  }
+  for (int k = nvec * 8 + threadIdx.x; k < V; k += blockDim.x) {
+    float o = __expf(__bfloat162float(lr[k]) - gm) * inv;
+    if (k == tgt) o -= grad_scale;
+    lr[k] = __float2bfloat16(o);
+  }
+}
+
+// ------------------------------- AdamW --------------------------------------
+// Flat multi-tensor AdamW: bf16 params + fp32 master/m/v, bf16 grads.
+// `gate` (nullable) points at a device int: the update is skipped entirely
+// when *gate == 0, which lets the launch be enqueued before the host has the
+// should_commit verdict (torchft/optim.py:52-55 semantics, no extra sync).
+struct AdamArgs {
+  bf16* p;
+  float* master;
+  float* m;
+  float* v;
+  const bf16* g;
+  size_t n;
+  float lr, b1, b2, eps, wd, bc1, bc2, gscale;
+  const int* gate;
+};
+
+__global__ void __launch_bounds__(512) adamw_kernel(AdamArgs a) {
+  if (a.gate != nullptr && *a.gate == 0) return;
+  const size_t nvec = a.n / 8;
+  const float step_size = a.lr / a.bc1;
+  const float inv_bc2_sqrt = rsqrtf(a.bc2);
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    float g[8], o[8];
+    P8::unpack(ld_stream(a.g + v * 8), g);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float w[4], m[4], vv[4];
+      Pack<float>::unpack(ld_stream(a.master + v * 8 + 4 * h), w);
+      Pack<float>::unpack(ld_stream(a.m + v * 8 + 4 * h), m);
+      Pack<float>::unpack(ld_stream(a.v + v * 8 + 4 * h), vv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gr = g[4 * h + k] * a.gscale;
+        m[k] = a.b1 * m[k] + (1.f - a.b1) * gr;
+        vv[k] = a.b2 * vv[k] + (1.f - a.b2) * gr * gr;
+        const float denom = sqrtf(vv[k]) * inv_bc2_sqrt + a.eps;
+        w[k] = w[k] * (1.f - a.lr * a.wd) - step_size * (m[k] / denom);
+        o[4 * h + k] = w[k];
+      }
+      st_stream(a.master + v * 8 + 4 * h, Pack<float>::pack(w));
+      st_stream(a.m + v * 8 + 4 * h, Pack<float>::pack(m));
+      st_stream(a.v + v * 8 + 4 * h, Pack<float>::pack(vv));
+    }
+    st_stream(a.p + v * 8, P8::pack(o));
+  }
+  if (blockIdx.x == 0) {
+    for (size_t k = nvec * 8 + threadIdx.x; k < a.n; k += blockDim.x) {
+      const float gr = __bfloat162float(a.g[k]) * a.gscale;
+      const float m = a.b1 * a.m[k] + (1.f - a.b1) * gr;
+      const float vv = a.b2 * a.v[k] + (1.f - a.b2) * gr * gr;
+      const float denom = sqrtf(vv) * inv_bc2_sqrt + a.eps;
+      const float w = a.master[k] * (1.f - a.lr * a.wd) - step_size * (m / denom);
+      a.m[k] = m;
+      a.v[k] = vv;
+      a.master[k] = w;
+      a.p[k] = __float2bfloat16(w);
+    }
+  }
+}
+
+// sum of squares of a bf16 buffer -> out[0] (+=), for grad-norm clipping
+__global__ void __launch_bounds__(512) sumsq_kernel(const bf16* __restrict__ g, size_t n,
+                                                    float* __restrict__ out) {
+  __shared__ float red[32];
+  const size_t nvec = n / 8;
+  float s = 0.f;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    float f[8];
+    P8::unpack(ld_stream(g + v * 8), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += f[k] * f[k];
+  }
+  if (blockIdx.x == 0) {
+    for (size_t k = nvec * 8 + threadIdx.x; k < n; k += blockDim.x) {
+      const float x = __bfloat162float(g[k]);
+      s += x * x;
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// ------------------------------- heal copy ----------------------------------
+// Live-recovery transport: stream state_dict shards GPU->GPU over NVLink from
+// inside a kernel (reference moves them GPU->CPU->TCP->CPU->GPU,
+// torchft/checkpointing/http_transport.py:219-284). Each table entry is one
+// contiguous byte range; CTAs stride over fixed-size chunks of all entries.
+struct CopyEntry {
+  const char* src;
+  char* dst;
+  size_t bytes;
+  size_t chunk0;  // index of this entry's first chunk
+};
+
+__global__ void __launch_bounds__(512) heal_copy_kernel(const CopyEntry* __restrict__ table,
+                                                        int nentries, size_t total_chunks,
+                                                        size_t chunk_bytes) {
+  for (size_t c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+    // binary search for the entry containing chunk c
+    int lo = 0, hi = nentries - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].chunk0 <= c) lo = mid; else hi = mid - 1;
+    }
+    const CopyEntry e = table[lo];
+    const size_t start = (c - e.chunk0) * chunk_bytes;
+    const size_t end = min(start + chunk_bytes, e.bytes);
+    const char* s = e.src + start;
+    char* d = e.dst + start;
+    const size_t len = end - start;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      const size_t nv = len / 16;
+      for (size_t v = threadIdx.x; v < nv; v += blockDim.x) st_stream(d + v * 16, ld_stream(s + v * 16));
+      for (size_t k = nv * 16 + threadIdx.x; k < len; k += blockDim.x) d[k] = s[k];
+    } else {
+      for (size_t k = threadIdx.x; k < len; k += blockDim.x) d[k] = s[k];
+    }
+  }
+}
+
+// ------------------------------- launchers ----------------------------------
+static int grid_for(size_t work_items, int threads, int cap = 148 * 8) {
+  size_t g = (work_items + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > (size_t)cap) g = cap;
+  return (int)g;
+}
+
+void rmsnorm_fwd_launch(const void* x, const void* w, void* y, float* rstd, int rows, int H,
+                        float eps, cudaStream_t s) {
+  if (H % 8 || H > 8 * kRmsMaxVec * 512) throw std::runtime_error("rmsnorm: H must be %8 and <= 16384");
+  const int grid = rows < 148 * 8 ? rows : 148 * 8;
+  const int nv = (H / 8 + 511) / 512;
+  if (nv <= 1)
+    rmsnorm_fwd_kernel<1><<<grid, 512, 0, s>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
+  else if (nv <= 2)
+    rmsnorm_fwd_kernel<2><<<grid, 512, 0, s>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
+  else
+    rmsnorm_fwd_kernel<4><<<grid, 512, 0, s>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+int rmsnorm_bwd_grid(int rows) { return rows < 296 ? rows : 296; }
+
+void rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                        float* dw_partial, void* dw, int accumulate, int rows, int H,
+                        cudaStream_t s) {
+  if (H % 8 || H > 8 * kRmsMaxVec * 512) throw std::runtime_error("rmsnorm: H must be %8 and <= 16384");
+  const int grid = rmsnorm_bwd_grid(rows);
+  const int nv = (H / 8 + 511) / 512;
+  if (nv <= 1)
+    rmsnorm_bwd_kernel<1><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
+                                               (bf16*)dx, dw_partial, rows, H);
+  else if (nv <= 2)
+    rmsnorm_bwd_kernel<2><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
+                                               (bf16*)dx, dw_partial, rows, H);
+  else
+    rmsnorm_bwd_kernel<4><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
+                                               (bf16*)dx, dw_partial, rows, H);
+  colsum_kernel<<<(H + 255) / 256, 256, 0, s>>>(dw_partial, grid, H, (bf16*)dw, accumulate);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void swiglu_fwd_launch(const void* gu, void* y, size_t T, int F, cudaStream_t s) {
+  if (F % 8) throw std::runtime_error("swiglu: F must be a multiple of 8");
+  swiglu_fwd_kernel<<<grid_for(T * (F / 8), 512), 512, 0, s>>>((const bf16*)gu, (bf16*)y, T, F);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+void swiglu_bwd_launch(const void* dy, const void* gu, void* dgu, size_t T, int F, cudaStream_t s) {
+  if (F % 8) throw std::runtime_error("swiglu: F must be a multiple of 8");
+  swiglu_bwd_kernel<<<grid_for(T * (F / 8), 512), 512, 0, s>>>((const bf16*)dy, (const bf16*)gu,
+                                                               (bf16*)dgu, T, F);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void rope_launch(const void* in, void* out, const void* cs, size_t T, int S, int heads, int D,
+                 size_t in_stride, size_t out_stride, float sign, cudaStream_t s) {
+  if (D % 8) throw std::runtime_error("rope: head_dim must be a multiple of 8");
+  rope_kernel<<<grid_for(T * heads * (D / 8), 256), 256, 0, s>>>(
+      (const bf16*)in, (bf16*)out, (const float2*)cs, T, S, heads, D, in_stride, out_stride, sign);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void xent_launch(void* logits, const void* target, float* loss, size_t rows, int V,
+                 size_t row_stride, float grad_scale, long long ignore_index, cudaStream_t s) {
+  if (row_stride % 8) throw std::runtime_error("xent: row stride must be a multiple of 8");
+  if (rows == 0) return;
+  xent_fwd_bwd_kernel<<<(unsigned)rows, 1024, 0, s>>>((bf16*)logits, (const long long*)target, loss,
+                                                      V, row_stride, grad_scale, ignore_index);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void adamw_launch(void* p, float* master, float* m, float* v, const void* g, size_t n, float lr,
+                  float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
+                  const int* gate, cudaStream_t s) {
+  AdamArgs a{(bf16*)p, master, m, v, (const bf16*)g, n, lr, b1, b2, eps, wd, bc1, bc2, gscale, gate};
+  adamw_kernel<<<grid_for(n / 8 + 1, 512, 148 * 4), 512, 0, s>>>(a);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void sumsq_launch(const void* g, size_t n, float* out, cudaStream_t s) {
+  sumsq_kernel<<<grid_for(n / 8 + 1, 512, 148 * 4), 512, 0, s>>>((const bf16*)g, n, out);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void heal_copy_launch(const void* table_dev, int nentries, size_t total_chunks, size_t chunk_bytes,
+                      int blocks, cudaStream_t s) {
+  if (total_chunks == 0) return;
+  if (blocks < 1) blocks = 1;
+  heal_copy_kernel<<<blocks, 512, 0, s>>>((const CopyEntry*)table_dev, nentries, total_chunks,
+                                          chunk_bytes);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace tft
