@@ -1,0 +1,183 @@
+"""Numerics of the hand-written sm_100a kernels vs plain PyTorch fp32 references."""
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    from torchft_b200.ops import _native
+
+    return _native.load()
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("rows,H", [(7, 256), (33, 4096), (5, 8192), (3, 16384)])
+def test_rmsnorm_fwd_bwd(rows, H):
+    from torchft_b200.ops import fused
+
+    torch.manual_seed(0)
+    x = torch.randn(rows, H, device="cuda").bfloat16().requires_grad_()
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).bfloat16().requires_grad_()
+    y = fused.rmsnorm(x, w, 1e-5)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf, wf = x.detach().float().requires_grad_(), w.detach().float().requires_grad_()
+    yf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    yf.backward(dy.float())
+    assert _rel(y, yf) < 1e-2
+    assert _rel(x.grad, xf.grad) < 1e-2
+    assert _rel(w.grad, wf.grad) < 2e-2
+
+
+def test_swiglu_fwd_bwd():
+    from torchft_b200.ops import fused
+
+    torch.manual_seed(1)
+    gu = torch.randn(37, 2 * 192, device="cuda").bfloat16().requires_grad_()
+    y = fused.swiglu(gu)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    g = gu.detach().float().requires_grad_()
+    yf = torch.nn.functional.silu(g[:, :192]) * g[:, 192:]
+    yf.backward(dy.float())
+    assert _rel(y, yf) < 1e-2
+    assert _rel(gu.grad, g.grad) < 1e-2
+
+
+def test_rope_qkv_matches_complex_rotation():
+    from torchft_b200.ops import fused
+
+    torch.manual_seed(2)
+    B, S, Hq, Hkv, D = 2, 16, 4, 2, 32
+    qkv = torch.randn(B * S, (Hq + 2 * Hkv) * D, device="cuda").bfloat16().requires_grad_()
+    cs = fused.rope_table(S, D, 10000.0, qkv.device)
+    q, k, v = fused.rope_qkv(qkv, cs, B, S, Hq, Hkv, D)
+
+    def ref_rot(x):  # x [B,S,H,D] fp32
+        xc = torch.view_as_complex(x.reshape(*x.shape[:-1], D // 2, 2))
+        f = torch.polar(torch.ones(S, D // 2, device=x.device), torch.outer(
+            torch.arange(S, device=x.device).float(),
+            1.0 / (10000.0 ** (torch.arange(0, D, 2, device=x.device).float() / D))))
+        return torch.view_as_real(xc * f[None, :, None, :]).reshape(x.shape)
+
+    ref = qkv.detach().float().requires_grad_()
+    r3 = ref.view(B, S, Hq + 2 * Hkv, D)
+    qf, kf, vf = ref_rot(r3[:, :, :Hq]), ref_rot(r3[:, :, Hq:Hq + Hkv]), r3[:, :, Hq + Hkv:]
+    assert _rel(q, qf) < 1e-2 and _rel(k, kf) < 1e-2 and _rel(v, vf) < 1e-6
+    dq, dk, dv = torch.randn_like(q), torch.randn_like(k), torch.randn_like(v)
+    torch.autograd.backward([q, k, v], [dq, dk, dv])
+    torch.autograd.backward([qf, kf, vf], [dq.float(), dk.float(), dv.float()])
+    assert _rel(qkv.grad, ref.grad) < 1e-2
+
+
+@pytest.mark.parametrize("T,V", [(64, 1000), (33, 4104), (16, 128256)])
+def test_linear_cross_entropy(T, V):
+    from torchft_b200.ops import fused
+
+    torch.manual_seed(3)
+    H = 128
+    h = (torch.randn(T, H, device="cuda") * 0.5).bfloat16().requires_grad_()
+    W = (torch.randn(V, H, device="cuda") * 0.05).bfloat16().requires_grad_()
+    tgt = torch.randint(0, V, (T,), device="cuda")
+    loss = fused.linear_cross_entropy(h, W, tgt, chunk=24, count_valid=False)
+    loss.backward()
+    hf, Wf = h.detach().float().requires_grad_(), W.detach().float().requires_grad_()
+    lf = torch.nn.functional.cross_entropy(hf @ Wf.t(), tgt)
+    lf.backward()
+    assert abs(loss.item() - lf.item()) < 2e-2 * max(1.0, abs(lf.item()))
+    assert _rel(h.grad, hf.grad) < 3e-2
+    assert _rel(W.grad, Wf.grad) < 3e-2
+
+
+def test_cross_entropy_inplace_ignore_index():
+    from torchft_b200.ops import fused
+
+    torch.manual_seed(4)
+    logits = torch.randn(8, 512, device="cuda").bfloat16()
+    tgt = torch.randint(0, 512, (8,), device="cuda")
+    tgt[3] = -100
+    ref = torch.nn.functional.cross_entropy(logits.float(), tgt, reduction="none", ignore_index=-100)
+    losses = fused.cross_entropy_inplace(logits, tgt, 1.0)
+    assert torch.allclose(losses, ref, atol=2e-2, rtol=2e-2)
+    assert logits[3].abs().max().item() == 0.0
+
+
+def test_flat_adamw_matches_torch():
+    from torchft_b200.ops import fused
+
+    torch.manual_seed(5)
+    n = 10007
+    p = torch.randn(n, device="cuda").bfloat16()
+    g = torch.zeros_like(p)
+    opt = fused.FlatAdamW(p, g, lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    ref_p = p.float().clone().requires_grad_()
+    ref = torch.optim.AdamW([ref_p], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    gate = torch.ones(1, dtype=torch.int32, device="cuda")
+    for step in range(5):
+        gr = torch.randn(n, device="cuda").bfloat16()
+        g.copy_(gr)
+        ref_p.grad = gr.float()
+        opt.step(gate=gate)
+        ref.step()
+    assert _rel(opt.master, ref_p.detach()) < 1e-5
+    assert _rel(p, ref_p.detach()) < 5e-3
+    before = opt.master.clone()
+    gate.zero_()
+    opt.step(gate=gate)  # gated off: must be a no-op
+    assert torch.equal(before, opt.master)
+    ss = opt.grad_sumsq()
+    assert abs(ss.item() - g.float().pow(2).sum().item()) < 1e-2 * ss.item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n", [5, 512, 100003])
+def test_q8_roundtrip(K, dtype, n):
+    from torchft_b200 import quantization as Q
+
+    torch.manual_seed(6)
+    x = (torch.randn(n, device="cuda") * 10).to(dtype)
+    buf = Q.quantize_q8(x, world_size=2)
+    y = Q.dequantize_q8(buf, n, dtype, world_size=2)
+    rel = ((y.float() - x.float()).abs().mean() / x.float().abs().mean()).item()
+    assert rel < 0.04
+
+
+def test_heal_copy(K):
+    from torchft_b200.checkpointing.p2p_transport import device_copy
+
+    torch.manual_seed(7)
+    srcs = [torch.randn(n, device="cuda") for n in (1, 1000, 1 << 20, 12345)]
+    srcs.append(torch.randint(0, 255, (777,), device="cuda", dtype=torch.uint8)[1:])  # unaligned
+    dsts = [torch.empty_like(s) for s in srcs]
+    device_copy([(s.data_ptr(), d.data_ptr(), s.numel() * s.element_size()) for s, d in zip(srcs, dsts)])
+    torch.cuda.synchronize()
+    for s, d in zip(srcs, dsts):
+        assert torch.equal(s, d)
+
+
+def test_llama_tiny_fwd_bwd_matches_reference():
+    from torchft_b200.models.llama import CONFIGS, Llama
+    from torchft_b200.models.reference import reference_loss
+
+    torch.manual_seed(8)
+    cfg = CONFIGS["llama3_tiny"]
+    m = Llama(cfg, device="cuda")
+    m.init_weights(0)
+    tok = torch.randint(0, cfg.vocab_size, (2, 64), device="cuda")
+    tgt = torch.randint(0, cfg.vocab_size, (2, 64), device="cuda")
+    loss = m(tok, tgt)
+    loss.backward()
+    ref_loss, ref_grads = reference_loss(m, tok, tgt)
+    assert abs(loss.item() - ref_loss) < 3e-2 * max(1.0, abs(ref_loss))
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        r = _rel(p.grad, ref_grads[name])
+        assert r < 0.1, (name, r)

@@ -1,0 +1,199 @@
+"""Llama-3 family decoder for the fault-tolerant training benchmarks.
+
+The reference ships no model: its flagship config (BASELINE.json, "Llama-3 8B
+fault-tolerant HSDP bf16") borrows torchtitan's. This is our own B200-first
+implementation, laid out for one-GPU-per-replica training in 180 GB of HBM3e:
+
+* every parameter is a view into ONE flat bf16 buffer and every gradient a view
+  into ONE flat bf16 gradient buffer that can live in NVLink-symmetric memory,
+  so the cross-replica all-reduce kernel reads gradients in place (zero copy)
+  and AdamW is a single launch over the whole model;
+* q/k/v and gate/up projections are fused GEMMs (cuBLAS);
+* RMSNorm, RoPE(+qkv split), SwiGLU, softmax-cross-entropy and AdamW are
+  hand-written sm_100a kernels (``torchft_b200/csrc/kernels/model_ops.cu``);
+* normalised activations and the SwiGLU product are recomputed in backward
+  instead of stored (see ``ops.fused.norm_linear`` / ``swiglu_linear``);
+* attention is the SDPA library kernel (flash / cuDNN), causal, GQA.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+from typing import Callable, Dict, Iterator, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from torchft_b200.ops import fused
+
+
+@dataclass
+class LlamaConfig:
+    dim: int = 4096
+    n_layers: int = 32
+    n_heads: int = 32
+    n_kv_heads: int = 8
+    vocab_size: int = 128256
+    ffn_dim: int = 14336
+    norm_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    max_seq_len: int = 8192
+    # "none": keep activations (fused recompute only); "full": checkpoint every block
+    activation_checkpoint: str = "none"
+    loss_chunk: int = 2048
+
+    @property
+    def head_dim(self) -> int:
+        return self.dim // self.n_heads
+
+    def num_params(self) -> int:
+        d, f, v = self.dim, self.ffn_dim, self.vocab_size
+        qkv = (self.n_heads + 2 * self.n_kv_heads) * self.head_dim * d
+        per_layer = qkv + d * d + 2 * f * d + f * d + 2 * d
+        return 2 * v * d + self.n_layers * per_layer + d
+
+    def flops_per_token(self, seq_len: int) -> float:
+        """Training FLOPs/token: 6 * matmul params + causal attention (fwd+bwd)."""
+        d, f, v = self.dim, self.ffn_dim, self.vocab_size
+        qkv = (self.n_heads + 2 * self.n_kv_heads) * self.head_dim * d
+        mm = self.n_layers * (qkv + d * d + 3 * f * d) + v * d
+        attn = self.n_layers * 2 * 2 * seq_len * d / 2  # QK^T and PV, causal half
+        return 6.0 * mm + 3.0 * attn
+
+
+CONFIGS: Dict[str, LlamaConfig] = {
+    "llama3_8b": LlamaConfig(),
+    "llama3_1b": LlamaConfig(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, ffn_dim=8192),
+    "llama3_debug": LlamaConfig(dim=256, n_layers=2, n_heads=8, n_kv_heads=2, vocab_size=2048, ffn_dim=768, max_seq_len=512),
+    "llama3_tiny": LlamaConfig(dim=64, n_layers=2, n_heads=4, n_kv_heads=2, vocab_size=512, ffn_dim=192, max_seq_len=128),
+}
+
+
+class Block(nn.Module):
+    def __init__(self, cfg: LlamaConfig, device=None, dtype=torch.bfloat16) -> None:
+        super().__init__()
+        d, hd = cfg.dim, cfg.head_dim
+        kw = dict(device=device, dtype=dtype)
+        self.cfg = cfg
+        self.attention_norm = nn.Parameter(torch.empty(d, **kw))
+        self.wqkv = nn.Parameter(torch.empty((cfg.n_heads + 2 * cfg.n_kv_heads) * hd, d, **kw))
+        self.wo = nn.Parameter(torch.empty(d, d, **kw))
+        self.ffn_norm = nn.Parameter(torch.empty(d, **kw))
+        self.w13 = nn.Parameter(torch.empty(2 * cfg.ffn_dim, d, **kw))
+        self.w2 = nn.Parameter(torch.empty(d, cfg.ffn_dim, **kw))
+
+    def forward(self, x: torch.Tensor, cs: torch.Tensor) -> torch.Tensor:
+        cfg = self.cfg
+        B, S, d = x.shape
+        qkv = fused.norm_linear(x, self.attention_norm, self.wqkv, cfg.norm_eps)
+        q, k, v = fused.rope_qkv(qkv.view(B * S, -1), cs, B, S, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
+        o = F.scaled_dot_product_attention(
+            q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True,
+            enable_gqa=cfg.n_kv_heads != cfg.n_heads,
+        )
+        o = o.transpose(1, 2).reshape(B, S, d)
+        h = x + o @ self.wo.t()
+        gu = fused.norm_linear(h, self.ffn_norm, self.w13, cfg.norm_eps)
+        return h + fused.swiglu_linear(gu, self.w2)
+
+
+class Llama(nn.Module):
+    def __init__(self, cfg: LlamaConfig, device=None, dtype=torch.bfloat16) -> None:
+        super().__init__()
+        self.cfg = cfg
+        kw = dict(device=device, dtype=dtype)
+        self.tok_embeddings = nn.Parameter(torch.empty(cfg.vocab_size, cfg.dim, **kw))
+        self.layers = nn.ModuleList(Block(cfg, device=device, dtype=dtype) for _ in range(cfg.n_layers))
+        self.norm = nn.Parameter(torch.empty(cfg.dim, **kw))
+        self.output = nn.Parameter(torch.empty(cfg.vocab_size, cfg.dim, **kw))
+        self._cs: Optional[torch.Tensor] = None
+
+    @torch.no_grad()
+    def init_weights(self, seed: int = 0) -> None:
+        """Deterministic random init (same on every replica for a given seed)."""
+        gen = torch.Generator(device=self.tok_embeddings.device)
+        gen.manual_seed(seed)
+        std = 0.02
+        for name, p in self.named_parameters():
+            if name.endswith("norm"):
+                p.fill_(1.0)
+            else:
+                s = std / math.sqrt(2 * self.cfg.n_layers) if name.endswith(("wo", "w2")) else std
+                p.normal_(0.0, s, generator=gen)
+
+    def rope_cache(self, seq_len: int, device: torch.device) -> torch.Tensor:
+        if self._cs is None or self._cs.shape[0] < seq_len or self._cs.device != device:
+            self._cs = fused.rope_table(max(seq_len, 1), self.cfg.head_dim, self.cfg.rope_theta, device)
+        return self._cs
+
+    def hidden(self, tokens: torch.Tensor) -> torch.Tensor:
+        B, S = tokens.shape
+        cs = self.rope_cache(S, tokens.device)
+        x = F.embedding(tokens, self.tok_embeddings)
+        for blk in self.layers:
+            if self.cfg.activation_checkpoint == "full" and torch.is_grad_enabled():
+                from torch.utils.checkpoint import checkpoint
+
+                x = checkpoint(blk, x, cs, use_reentrant=False)
+            else:
+                x = blk(x, cs)
+        return x
+
+    def forward(self, tokens: torch.Tensor, targets: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Returns the mean next-token loss when ``targets`` is given, else logits."""
+        x = self.hidden(tokens)
+        B, S, d = x.shape
+        if targets is None:
+            return fused.rmsnorm(x, self.norm, self.cfg.norm_eps) @ self.output.t()
+        h = fused.rmsnorm(x, self.norm, self.cfg.norm_eps).view(B * S, d)
+        return fused.linear_cross_entropy(h, self.output, targets.reshape(-1), chunk=self.cfg.loss_chunk, count_valid=False)
+
+
+class FlatParams:
+    """Re-home a module's parameters (and gradients) into two flat bf16 buffers.
+
+    ``grad_alloc(numel) -> Tensor`` lets the caller place the gradient buffer in
+    NVLink-symmetric memory (``ProcessGroupB200.alloc_symmetric``); buckets for
+    the overlapped cross-replica all-reduce are contiguous slices of it.
+    Parameters are laid out in REVERSE registration order so that buckets fill
+    front-to-back in the order backward produces gradients.
+    """
+
+    ALIGN = 128  # elements; keeps every view 256 B aligned
+
+    def __init__(self, module: nn.Module, grad_alloc: Optional[Callable[[int], torch.Tensor]] = None) -> None:
+        params = [p for p in module.parameters() if p.requires_grad]
+        assert params, "module has no parameters"
+        dev, dt = params[0].device, params[0].dtype
+        order = list(reversed(params))
+        offs, total = [], 0
+        for p in order:
+            offs.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = total
+        self.param = torch.zeros(total, dtype=dt, device=dev)
+        self.grad = grad_alloc(total) if grad_alloc is not None else torch.zeros(total, dtype=dt, device=dev)
+        assert self.grad.numel() >= total and self.grad.dtype == dt
+        self.grad = self.grad[:total]
+        self.params: List[nn.Parameter] = order
+        self.offsets: List[int] = offs
+        with torch.no_grad():
+            for p, o in zip(order, offs):
+                v = self.param[o : o + p.numel()].view_as(p)
+                v.copy_(p.data)
+                p.data = v
+                p.grad = self.grad[o : o + p.numel()].view_as(p)
+
+    def buckets(self, bucket_elems: int) -> List[Tuple[int, int, List[nn.Parameter]]]:
+        """Contiguous (start, end, params) buckets in gradient-production order."""
+        out: List[Tuple[int, int, List[nn.Parameter]]] = []
+        start, cur = 0, []
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            cur.append(p)
+            end = self.offsets[i + 1] if i + 1 < len(self.params) else self.numel
+            if end - start >= bucket_elems or i + 1 == len(self.params):
+                out.append((start, end, cur))
+                start, cur = end, []
+        return out

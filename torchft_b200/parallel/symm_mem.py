@@ -1,0 +1,355 @@
+"""NVLink peer-memory manager + collectives for one replica-group rank.
+
+This is the B200-native replacement for "destroy and re-create the NCCL
+communicator on every quorum change" (reference:
+torchft/process_group.py:435-471,848-873). The CUDA context, streams, local
+segments and the signal pad survive reconfiguration; ``configure()`` only
+
+1. publishes this rank's segment descriptors (CUDA IPC handles) under the
+   per-quorum store prefix,
+2. maps segments of peers that are NEW to the quorum and unmaps those that left
+   (handles of surviving peers are cached and reused), and
+3. agrees on a flag floor so the epoch-tagged signal protocol restarts cleanly.
+
+Failure containment: every in-kernel wait is a bounded, abortable spin on a
+host-mapped status block (see ``csrc/kernels/common.cuh``), so a dead peer
+produces a latched error (``errored()``) rather than a wedged stream --
+the analogue of ``ncclCommAbort`` without tearing anything down.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import socket
+import threading
+from dataclasses import dataclass, field
+from datetime import timedelta
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from torchft_b200.ops import _native
+
+_CH_ALLREDUCE = 0
+_CH_Q8 = 1
+_CH_HEAL = 2
+_CH_USER = 3
+
+_ALIGN = 2 << 20  # segment sizes rounded to 2 MiB (TLB page granularity on Blackwell)
+
+
+class _CAI:
+    """Minimal ``__cuda_array_interface__`` carrier to view raw device memory as a tensor."""
+
+    def __init__(self, ptr: int, nbytes: int) -> None:
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,),
+            "typestr": "|u1",
+            "data": (ptr, False),
+            "version": 3,
+            "strides": None,
+        }
+
+
+def tensor_from_ptr(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor:
+    return torch.as_tensor(_CAI(ptr, nbytes), device=device)
+
+
+@dataclass
+class Segment:
+    """A cudaMalloc'ed region exported to peers over CUDA IPC."""
+
+    name: str
+    ptr: int
+    nbytes: int
+    handle: bytes
+    tensor: torch.Tensor  # uint8 view keeping python-side references simple
+
+    def contains(self, p: int, n: int) -> bool:
+        return self.ptr <= p and p + n <= self.ptr + self.nbytes
+
+
+class SymmetricComm:
+    """Peer-memory communicator over the current healthy replica set."""
+
+    def __init__(
+        self,
+        device: Optional[torch.device] = None,
+        staging_bytes: Optional[int] = None,
+        timeout: timedelta = timedelta(seconds=60),
+    ) -> None:
+        self._K = _native.load()
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._lock = threading.RLock()
+        self._status = None
+        self._segments: Dict[str, Segment] = {}
+        self._peer_ptrs: Dict[Tuple[str, int, bytes], int] = {}  # (host, pid, handle) -> mapped ptr
+        self._tables: Dict[str, Any] = {}
+        self._rank = 0
+        self._world = 1
+        self._epoch = 0
+        self._flag = 0
+        self._configured = False
+        self._timeout = timeout
+        if staging_bytes is None:
+            staging_bytes = int(os.environ.get("TORCHFT_B200_STAGING_MB", "256")) << 20
+        self._staging_bytes = (staging_bytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        self._pad_bytes = (self._K.SIGNAL_PAD_BYTES + 65535) // 65536 * 65536
+        self._max_blocks = int(os.environ.get("TORCHFT_B200_AR_BLOCKS", "64"))
+        self._threads = int(os.environ.get("TORCHFT_B200_AR_THREADS", "512"))
+        self._oneshot_max = int(os.environ.get("TORCHFT_B200_ONESHOT_KB", "256")) << 10
+        self.launches = 0  # native kernel launches issued (bench reports this)
+        self._hostname = socket.gethostname()
+
+    # ------------------------------------------------------------------ memory
+    def _ensure_core(self) -> None:
+        if self._status is None:
+            with torch.cuda.device(self.device):
+                self._status = self._K.Status()
+                self._status.set_timeout_ms(self._timeout.total_seconds() * 1e3)
+                self._alloc_segment("core", self._pad_bytes + self._staging_bytes)
+
+    def _alloc_segment(self, name: str, nbytes: int) -> Segment:
+        nbytes = (nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        with torch.cuda.device(self.device):
+            ptr = self._K.symm_alloc(nbytes)
+            handle = self._K.ipc_get_handle(ptr)
+        seg = Segment(name, ptr, nbytes, handle, tensor_from_ptr(ptr, nbytes, self.device))
+        self._segments[name] = seg
+        return seg
+
+    def alloc(self, name: str, nbytes: int) -> torch.Tensor:
+        """Allocate a symmetric (peer-visible) segment; returns a uint8 tensor.
+
+        Must be called with the same ``name``/``nbytes`` on every replica before the
+        next ``configure()``; tensors carved from it are all-reduced zero-copy.
+        """
+        with self._lock:
+            self._ensure_core()
+            if name in self._segments:
+                raise ValueError(f"symmetric segment {name!r} already exists")
+            seg = self._alloc_segment(name, nbytes)
+            self._configured = self._configured and self._world == 1
+            return seg.tensor[:nbytes]
+
+    def set_timeout(self, timeout: timedelta) -> None:
+        self._timeout = timeout
+        if self._status is not None:
+            self._status.set_timeout_ms(timeout.total_seconds() * 1e3)
+
+    # --------------------------------------------------------------- configure
+    def configure(self, store: Any, rank: int, world: int, epoch: int) -> None:
+        """(Re)map peer memory for a new quorum. ``store`` is any c10d Store scoped to the quorum."""
+        K = self._K
+        with self._lock:
+            self._ensure_core()
+            with torch.cuda.device(self.device):
+                # Drain in-flight collectives of the old quorum (they either
+                # finished or bailed out through the abort flag).
+                torch.cuda.synchronize(self.device)
+                self._status.clear()
+                desc = {
+                    "host": self._hostname,
+                    "pid": os.getpid(),
+                    "device": self.device.index,
+                    "floor": self._flag,
+                    "segments": {n: {"handle": s.handle.hex(), "nbytes": s.nbytes} for n, s in self._segments.items()},
+                }
+                store.set(f"symm/{rank}", json.dumps(desc))
+                descs: List[Dict[str, Any]] = []
+                for r in range(world):
+                    descs.append(desc if r == rank else json.loads(bytes(store.get(f"symm/{r}")).decode()))
+                names = sorted(self._segments)
+                for r, d in enumerate(descs):
+                    if sorted(d["segments"]) != names:
+                        raise RuntimeError(f"rank {r} registered segments {sorted(d['segments'])}, expected {names}")
+                    for n in names:
+                        if d["segments"][n]["nbytes"] != self._segments[n].nbytes:
+                            raise RuntimeError(f"segment {n!r} size mismatch on rank {r}")
+                needed: Dict[Tuple[str, int, bytes], int] = {}
+                ptrs: Dict[str, List[int]] = {n: [] for n in names}
+                for r, d in enumerate(descs):
+                    for n in names:
+                        if r == rank:
+                            ptrs[n].append(self._segments[n].ptr)
+                            continue
+                        h = bytes.fromhex(d["segments"][n]["handle"])
+                        key = (d["host"], int(d["pid"]), h)
+                        if d["host"] != self._hostname:
+                            raise RuntimeError("peer-memory transport requires all replicas on one NVSwitch domain (same host)")
+                        p = self._peer_ptrs.get(key)
+                        if p is None:
+                            p = K.ipc_open_handle(h)
+                        needed[key] = p
+                        ptrs[n].append(p)
+                # unmap peers that left the quorum
+                for key, p in list(self._peer_ptrs.items()):
+                    if key not in needed:
+                        try:
+                            K.ipc_close_handle(p)
+                        except RuntimeError:
+                            pass  # exporter already gone
+                self._peer_ptrs = needed
+                core_ptrs = ptrs["core"]
+                pads = core_ptrs  # signal pad sits at offset 0 of the core segment
+                self._tables = {}
+                base = K.PeerTable([p + self._pad_bytes for p in core_ptrs], pads, rank, world)
+                self._tables["core"] = base
+                for n in names:
+                    if n != "core":
+                        self._tables[n] = base.with_data(ptrs[n])
+                floor = max(int(d["floor"]) for d in descs)
+                self._flag = max(floor, int(epoch) << 32) + 16
+                self._rank, self._world, self._epoch = rank, world, int(epoch)
+                self._configured = True
+
+    # ------------------------------------------------------------- collectives
+    def _plan(self, nbytes: int) -> Tuple[int, int]:
+        """(algo, blocks): identical on every rank for a given message size."""
+        if nbytes <= self._oneshot_max // max(1, self._world // 4):
+            blocks = max(1, min(8, nbytes // (16 * self._threads * 2) + 1))
+            return 0, blocks
+        blocks = max(4, min(self._max_blocks, nbytes // (256 << 10)))
+        return 1, blocks
+
+    def _next_flag(self) -> int:
+        f = self._flag
+        self._flag += 2
+        return f
+
+    def _segment_of(self, t: torch.Tensor) -> Optional[Tuple[Segment, int]]:
+        p, n = t.data_ptr(), t.numel() * t.element_size()
+        for s in self._segments.values():
+            if s.contains(p, n):
+                return s, p - s.ptr
+        return None
+
+    def allreduce_(self, t: torch.Tensor, op: int = _native.OP_SUM, scale: float = 1.0,
+                   contribute: bool = True, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """In-place all-reduce of ``t`` over the current quorum on ``stream``.
+
+        ``scale`` is fused (1/num_participants for AVG); ``contribute=False`` makes
+        this rank add zeros (healing / spare replica) without touching ``t`` first.
+        """
+        K = self._K
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError("allreduce_ needs a contiguous CUDA tensor")
+        dt = _native.dtype_code(t)
+        sp = _native.stream_ptr(stream)
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            if self._world == 1 and scale == 1.0 and contribute:
+                return
+            es = t.element_size()
+            hit = self._segment_of(t)
+            if hit is not None and hit[0].name != "core" and hit[1] % 16 == 0:
+                seg, off = hit
+                n = t.numel()
+                algo, blocks = self._plan(n * es)
+                K.allreduce(self._tables[seg.name], self._status, off, 0, 0, n, dt, op, scale, self._next_flag(),
+                            _CH_ALLREDUCE, contribute, algo, blocks, self._threads, sp)
+                self.launches += 1
+                return
+            if t.data_ptr() % 16:
+                raise ValueError("allreduce_ needs a 16-byte aligned tensor")
+            max_elems = self._staging_bytes // es
+            flat = t.view(-1)
+            for lo in range(0, flat.numel(), max_elems):
+                n = min(max_elems, flat.numel() - lo)
+                algo, blocks = self._plan(n * es)
+                ptr = flat.data_ptr() + lo * es
+                K.allreduce(self._tables["core"], self._status, 0, ptr, ptr, n, dt, op, scale, self._next_flag(),
+                            _CH_ALLREDUCE, contribute, algo, blocks, self._threads, sp)
+                self.launches += 1
+
+    def q8_bytes(self, numel: int) -> int:
+        return self._K.q8_buffer_bytes(numel, max(self._world, 1))
+
+    def q8_allreduce_(self, out: torch.Tensor, a: torch.Tensor, b: Optional[torch.Tensor] = None,
+                      scale: float = 1.0, contribute: bool = True,
+                      stream: Optional[torch.cuda.Stream] = None) -> None:
+        """out = dequant(allreduce_fp8(quant(a - b))) * scale, one launch per staging chunk.
+
+        ``b`` (optional) fuses DiLoCo's pseudo-gradient ``original - local``
+        (reference: torchft/local_sgd.py:324-337); ``out`` may alias ``a``.
+        """
+        K = self._K
+        for x in (out, a) + ((b,) if b is not None else ()):
+            if not x.is_cuda or not x.is_contiguous() or x.data_ptr() % 16:
+                raise ValueError("q8_allreduce_ needs contiguous 16-byte aligned CUDA tensors")
+        dt = _native.dtype_code(a)
+        sp = _native.stream_ptr(stream)
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            if self._world == 1:
+                # degenerate quorum: exact arithmetic, no quantisation noise
+                res = a if b is None else a - b
+                if not contribute:
+                    out.zero_()
+                elif scale != 1.0:
+                    torch.mul(res, scale, out=out)
+                elif out.data_ptr() != res.data_ptr():
+                    out.copy_(res)
+                return
+            es = a.element_size()
+            # elements per launch such that the Q8G buffer fits in staging
+            per = (self._staging_bytes * 512 // 516) // (512 * self._world) * (512 * self._world) - 512 * self._world
+            fo, fa = out.view(-1), a.view(-1)
+            fb = b.view(-1) if b is not None else None
+            for lo in range(0, fa.numel(), per):
+                n = min(per, fa.numel() - lo)
+                blocks = max(4, min(self._max_blocks, (n // 512) // 64 + 1))
+                K.q8_allreduce(self._tables["core"], self._status, 0, fa.data_ptr() + lo * es,
+                               (fb.data_ptr() + lo * es) if fb is not None else 0, fo.data_ptr() + lo * es, n, dt,
+                               scale, self._next_flag(), _CH_Q8, contribute, blocks, sp)
+                self.launches += 1
+
+    # ------------------------------------------------------------------ status
+    def abort(self) -> None:
+        """Make every in-flight / future kernel wait bail out immediately."""
+        if self._status is not None:
+            self._status.set_abort(True)
+
+    def errored(self) -> Optional[Exception]:
+        if self._status is None:
+            return None
+        code, peer, seq = self._status.error()
+        if code == 0:
+            return None
+        what = {1: "timeout", 2: "aborted"}.get(code, f"error {code}")
+        return RuntimeError(f"peer-memory collective {what} waiting for replica rank {peer} (seq {seq})")
+
+    @property
+    def rank(self) -> int:
+        return self._rank
+
+    @property
+    def world(self) -> int:
+        return self._world
+
+    @property
+    def configured(self) -> bool:
+        return self._configured
+
+    def shutdown(self) -> None:
+        K = self._K
+        with self._lock:
+            if self._status is not None:
+                self._status.set_abort(True)
+            try:
+                torch.cuda.synchronize(self.device)
+            except RuntimeError:
+                pass
+            for p in self._peer_ptrs.values():
+                try:
+                    K.ipc_close_handle(p)
+                except RuntimeError:
+                    pass
+            self._peer_ptrs = {}
+            self._tables = {}
+            self._configured = False
+            # local segments are intentionally leaked until process exit if a
+            # peer may still have them mapped; free only the python views
