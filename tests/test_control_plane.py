@@ -1,0 +1,411 @@
+"""Spec tests for the C++ control plane.
+
+The scenario tables re-create the reference's Rust unit tests
+(/root/reference/src/lighthouse.rs:627-1111, src/manager.rs:656-1218) against
+our implementation through the pybind11 module: pure decision functions first,
+then real servers on loopback (port 0) driven by real clients.
+"""
+
+import threading
+import time
+import urllib.request
+from datetime import timedelta
+
+import pytest
+
+from torchft_b200 import _C
+
+HOUR = 60 * 60 * 1000
+
+
+def member(rid, step=1, shrink_only=False, commit_failures=0, address="", store=""):
+    return _C.QuorumMember(replica_id=rid, address=address, store_address=store, step=step, world_size=1,
+                           shrink_only=shrink_only, commit_failures=commit_failures)
+
+
+def quorum_of(ids, quorum_id=1, steps=None):
+    q = _C.Quorum()
+    q.quorum_id = quorum_id
+    q.participants = [member(i, step=(steps or {}).get(i, 1)) for i in ids]
+    return q
+
+
+# --------------------------------------------------------------- quorum_compute
+def test_quorum_join_timeout():
+    now = 10 * HOUR * 10
+    kw = dict(min_replicas=1, join_timeout_ms=HOUR, heartbeat_timeout_ms=5000)
+    met, reason = _C.quorum_compute(now, [], {}, None, **kw)
+    assert met is None
+    assert "New quorum not ready, only have 0 participants, need min_replicas 1 [0/0 participants healthy]" in reason
+
+    parts = [(now, member("a")), (now, member("b"))]
+    hb = {"a": now, "b": now}
+    met, reason = _C.quorum_compute(now, parts, hb, None, **kw)
+    assert met is not None, reason
+
+    hb["c"] = now  # healthy but not participating -> wait for it
+    met, reason = _C.quorum_compute(now, parts, hb, None, **kw)
+    assert met is None and "join timeout" in reason
+
+    parts[0] = (now - 10 * HOUR, member("a"))  # first joiner waited long enough
+    met, reason = _C.quorum_compute(now, parts, hb, None, **kw)
+    assert met is not None, reason
+    assert [m.replica_id for m in met] == ["a", "b"]
+
+
+def test_quorum_heartbeats():
+    now = 100 * HOUR
+    kw = dict(min_replicas=1, join_timeout_ms=0, heartbeat_timeout_ms=5000)
+    parts = [(now, member("a"))]
+    met, reason = _C.quorum_compute(now, parts, {"a": now}, None, **kw)
+    assert met is not None
+    assert "[1/1 participants healthy][1 heartbeating]" in reason
+
+    met, reason = _C.quorum_compute(now, parts, {"a": now - 10_000}, None, **kw)  # expired
+    assert met is None
+    assert "[0/1 participants healthy][0 heartbeating]" in reason
+
+    parts.append((now, member("b")))
+    met, reason = _C.quorum_compute(now, parts, {"a": now - 10_000, "b": now}, None, **kw)
+    assert met is not None, reason
+    assert [m.replica_id for m in met] == ["b"]
+
+
+def test_quorum_fast_prev_quorum():
+    now = 100 * HOUR
+    kw = dict(min_replicas=1, join_timeout_ms=HOUR, heartbeat_timeout_ms=5000)
+    parts = [(now, member("a"))]
+    hb = {"a": now, "b": now}
+    met, reason = _C.quorum_compute(now, parts, hb, None, **kw)
+    assert met is None, reason  # b heartbeats but has not joined; join timeout not reached
+
+    prev = quorum_of(["a"])
+    met, reason = _C.quorum_compute(now, parts, hb, prev, **kw)
+    assert met is not None and "Fast quorum found" in reason
+
+    # fast quorum may also grow
+    parts.append((now, member("b")))
+    met, reason = _C.quorum_compute(now, parts, hb, prev, **kw)
+    assert met is not None and [m.replica_id for m in met] == ["a", "b"]
+
+
+def test_quorum_shrink_only():
+    now = 100 * HOUR
+    kw = dict(min_replicas=1, join_timeout_ms=HOUR, heartbeat_timeout_ms=5000)
+    prev = quorum_of(["a", "b"])
+    parts = [(now, member("a", shrink_only=True)), (now, member("c", shrink_only=True))]
+    hb = {"a": now, "c": now}
+    met, reason = _C.quorum_compute(now, parts, hb, prev, **kw)
+    assert met is not None, reason
+    assert "[shrink_only=true]" in reason
+    assert [m.replica_id for m in met] == ["a"]
+
+
+def test_quorum_split_brain():
+    now = 100 * HOUR
+    kw = dict(min_replicas=1, join_timeout_ms=HOUR, heartbeat_timeout_ms=5000)
+    parts = [(now - 2 * HOUR, member("a"))]
+    hb = {"a": now, "b": now}
+    met, reason = _C.quorum_compute(now, parts, hb, None, **kw)
+    assert met is None
+    assert "New quorum not ready, only have 1 participants, need at least half of 2 healthy workers" in reason
+    parts.append((now - 2 * HOUR, member("b")))
+    met, reason = _C.quorum_compute(now, parts, hb, None, **kw)
+    assert met is not None, reason
+
+
+def test_quorum_changed():
+    a, b, c = member("1"), member("1"), member("2")
+    a.address, b.address = "x", "y"  # only ids matter
+    assert not _C.quorum_changed([a], [b])
+    assert _C.quorum_changed([a], [c])
+    assert _C.quorum_changed([a], [a, c])
+
+
+# --------------------------------------------------------- compute_quorum_results
+def _q(steps, commit_failures=None):
+    q = _C.Quorum()
+    q.quorum_id = 1
+    q.participants = [
+        member(f"replica_{i}", step=s, address=f"addr_{i}", store=f"store_addr_{i}",
+               commit_failures=(commit_failures or {}).get(i, 0))
+        for i, s in enumerate(steps)
+    ]
+    return q
+
+
+def test_compute_quorum_results_first_step():
+    q = _q([0, 0])
+    r = _C.compute_quorum_results("replica_0", 0, q, True)
+    assert (r.heal, r.replica_rank, r.recover_src_replica_rank, r.recover_dst_replica_ranks) == (False, 0, None, [1])
+    r = _C.compute_quorum_results("replica_1", 0, q, True)
+    assert (r.heal, r.replica_rank, r.recover_src_replica_rank, r.recover_dst_replica_ranks) == (True, 1, 0, [])
+    # shard rank 1 rotates the primary
+    r = _C.compute_quorum_results("replica_1", 1, q, True)
+    assert (r.heal, r.replica_rank, r.recover_src_replica_rank, r.recover_dst_replica_ranks) == (False, 1, None, [0])
+    assert r.store_address == "store_addr_1"
+
+
+def test_compute_quorum_results_recovery():
+    q = _q([0, 1, 0, 1, 0])
+    r = _C.compute_quorum_results("replica_0", 0, q, True)
+    assert r.heal and r.recover_src_manager_address == "addr_1" and r.recover_src_replica_rank == 1
+    assert r.recover_dst_replica_ranks == [] and r.max_step == 1 and r.max_world_size == 2
+    assert r.max_replica_rank is None and r.replica_world_size == 5
+    r = _C.compute_quorum_results("replica_1", 0, q, True)
+    assert not r.heal and r.recover_src_manager_address == "" and r.recover_dst_replica_ranks == [0, 4]
+    assert r.max_replica_rank == 0
+    r = _C.compute_quorum_results("replica_3", 0, q, True)
+    assert not r.heal and r.replica_rank == 3 and r.recover_dst_replica_ranks == [2] and r.max_replica_rank == 1
+    r = _C.compute_quorum_results("replica_1", 1, q, True)
+    assert not r.heal and r.recover_dst_replica_ranks == [2]
+    assert r.replica_ids == [f"replica_{i}" for i in range(5)]
+
+
+def test_compute_quorum_results_skip_init_sync():
+    q = _q([0, 0])
+    assert not _C.compute_quorum_results("replica_0", 0, q, True).heal
+    assert _C.compute_quorum_results("replica_1", 0, q, True).heal
+    assert not _C.compute_quorum_results("replica_1", 0, q, False).heal
+    q = _q([1, 0])
+    assert _C.compute_quorum_results("replica_1", 0, q, False).heal
+
+
+def test_compute_quorum_results_commit_failures_and_missing():
+    q = _q([0, 0], commit_failures={1: 2})
+    assert _C.compute_quorum_results("replica_0", 0, q, True).commit_failures == 2
+    with pytest.raises(RuntimeError, match="not participating"):
+        _C.compute_quorum_results("nope", 0, q, True)
+
+
+def test_backoff_schedule():
+    s = _C.backoff_schedule(20)
+    assert s[0] == 100 and abs(s[1] - 150) < 1e-6 and abs(s[2] - 225) < 1e-6
+    assert max(s) == 10000 and s == sorted(s)
+
+
+# ----------------------------------------------------------------- real servers
+@pytest.fixture
+def lighthouse():
+    lh = _C.LighthouseServer(bind="[::]:0", min_replicas=1, join_timeout_ms=100, quorum_tick_ms=10)
+    yield lh
+    lh.shutdown()
+
+
+def test_lighthouse_e2e(lighthouse):
+    c = _C.LighthouseClient(lighthouse.address(), timedelta(seconds=5))
+    c.heartbeat("foo")
+    t0 = time.time()
+    q = c.quorum("foo", timedelta(seconds=5), address="addr", store_address="store", step=10, world_size=1,
+                 data={"k": [1, 2]})
+    assert time.time() - t0 < 0.4  # single replica join < 0.4 s (reference: lighthouse_test.py:50-53)
+    assert q.quorum_id == 1 and len(q.participants) == 1
+    p = q.participants[0]
+    assert (p.replica_id, p.address, p.store_address, p.step, p.world_size) == ("foo", "addr", "store", 10, 1)
+    assert p.data == {"k": [1, 2]}
+    assert q.created.seconds > 1_600_000_000
+    # same membership -> same id
+    assert c.quorum("foo", timedelta(seconds=5)).quorum_id == 1
+
+
+def test_lighthouse_timeout_and_runtime_errors():
+    lh = _C.LighthouseServer(bind="[::]:0", min_replicas=2, join_timeout_ms=100)
+    try:
+        c = _C.LighthouseClient(lh.address(), timedelta(seconds=5))
+        t0 = time.time()
+        with pytest.raises(TimeoutError):
+            c.quorum("lonely", timedelta(milliseconds=200))
+        assert time.time() - t0 < 1.0
+    finally:
+        lh.shutdown()
+    with pytest.raises(TimeoutError):
+        _C.LighthouseClient("http://localhost:1", timedelta(milliseconds=300))
+
+
+def test_lighthouse_join_during_shrink():
+    """A joiner is excluded from a shrink_only round and admitted to the next one."""
+    lh = _C.LighthouseServer(bind="[::]:0", min_replicas=2, join_timeout_ms=1000, quorum_tick_ms=10)
+    try:
+        addr = lh.address()
+        c0 = _C.LighthouseClient(addr, timedelta(seconds=5))
+        c1 = _C.LighthouseClient(addr, timedelta(seconds=5))
+        c2 = _C.LighthouseClient(addr, timedelta(seconds=5))
+        out = {}
+
+        def ask(name, client, **kw):
+            out[name] = client.quorum(name, timedelta(seconds=10), **kw)
+
+        ts = [threading.Thread(target=ask, args=("replica0", c0)), threading.Thread(target=ask, args=("replica1", c1))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert out["replica0"].quorum_id == out["replica1"].quorum_id == 1
+        assert len(out["replica0"].participants) == 2
+
+        # shrink round: replica0 asks shrink_only while replica2 tries to join
+        t2 = threading.Thread(target=ask, args=("replica2", c2))
+        t2.start()
+        time.sleep(0.1)
+        ts = [threading.Thread(target=ask, args=("replica0", c0), kwargs=dict(shrink_only=True)),
+              threading.Thread(target=ask, args=("replica1", c1))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        ids = sorted(p.replica_id for p in out["replica0"].participants)
+        assert ids == ["replica0", "replica1"], ids
+        assert out["replica0"].quorum_id == 1  # membership unchanged -> id unchanged
+
+        # next (non-shrink) round admits replica2 and bumps the id
+        ts = [threading.Thread(target=ask, args=("replica0", c0)), threading.Thread(target=ask, args=("replica1", c1))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        t2.join()
+        assert sorted(p.replica_id for p in out["replica2"].participants) == ["replica0", "replica1", "replica2"]
+        assert out["replica2"].quorum_id == 2
+    finally:
+        lh.shutdown()
+
+
+def test_lighthouse_commit_failures_bump_quorum_id(lighthouse):
+    lhc = _C.LighthouseClient(lighthouse.address(), timedelta(seconds=5))
+    assert lhc.quorum("r", timedelta(seconds=5)).quorum_id == 1
+    assert lhc.quorum("r", timedelta(seconds=5)).quorum_id == 1
+    # commit failures travel through the manager path
+    ms = _C.ManagerServer(replica_id="r", lighthouse_addr=lighthouse.address(), hostname="localhost", bind="[::]:0",
+                          store_addr="s", world_size=1, heartbeat_interval=timedelta(milliseconds=50),
+                          connect_timeout=timedelta(seconds=5), quorum_retries=0)
+    try:
+        mc = _C.ManagerClient(ms.address(), timedelta(seconds=5))
+        a = mc._quorum(0, 0, "", False, timedelta(seconds=5), 0)
+        b = mc._quorum(0, 0, "", False, timedelta(seconds=5), 0)
+        assert a.quorum_id == b.quorum_id
+        c = mc._quorum(0, 0, "", False, timedelta(seconds=5), 2)
+        assert c.quorum_id == b.quorum_id + 1 and c.commit_failures == 2
+    finally:
+        ms.shutdown()
+
+
+def _manager(lh, rid, world_size=1, **kw):
+    return _C.ManagerServer(replica_id=rid, lighthouse_addr=lh.address(), hostname="localhost", bind="[::]:0",
+                            store_addr=f"store_{rid}", world_size=world_size,
+                            heartbeat_interval=timedelta(milliseconds=50), connect_timeout=timedelta(seconds=5),
+                            quorum_retries=kw.get("quorum_retries", 0))
+
+
+def test_manager_should_commit_barrier(lighthouse):
+    ms = _manager(lighthouse, "rep", world_size=2)
+    try:
+        def vote(rank, v, out):
+            c = _C.ManagerClient(ms.address(), timedelta(seconds=5))
+            out[rank] = c.should_commit(rank, 1, v, timedelta(seconds=5))
+
+        for votes, expect in (((True, True), True), ((True, False), False), ((True, True), True)):
+            out = {}
+            ts = [threading.Thread(target=vote, args=(r, v, out)) for r, v in enumerate(votes)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            assert out == {0: expect, 1: expect}
+        # a lone voter times out quickly (reference asserts < 1.0 s: manager_integ_test.py:555-567)
+        c = _C.ManagerClient(ms.address(), timedelta(seconds=5))
+        t0 = time.time()
+        with pytest.raises(TimeoutError):
+            c.should_commit(0, 1, True, timedelta(milliseconds=100))
+        assert time.time() - t0 < 1.0
+    finally:
+        ms.shutdown()
+
+
+def test_manager_quorum_heal_first_step_and_metadata(lighthouse):
+    m0, m1 = _manager(lighthouse, "rep_0"), _manager(lighthouse, "rep_1")
+    try:
+        res = {}
+
+        def run(i, m, step):
+            c = _C.ManagerClient(m.address(), timedelta(seconds=5))
+            res[i] = c._quorum(0, step, f"meta_{i}", False, timedelta(seconds=10), 0, True)
+
+        ts = [threading.Thread(target=run, args=(0, m0, 0)), threading.Thread(target=run, args=(1, m1, 0))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert res[0].replica_rank == 0 and not res[0].heal and res[0].recover_dst_replica_ranks == [1]
+        assert res[1].replica_rank == 1 and res[1].heal and res[1].recover_src_replica_rank == 0
+        assert res[1].recover_src_manager_address == m0.address()
+        assert res[0].store_address == res[1].store_address == "store_rep_0"
+        assert res[0].replica_ids == ["rep_0", "rep_1"]
+        # healer looks up the source's transport metadata through the source's manager
+        c = _C.ManagerClient(res[1].recover_src_manager_address, timedelta(seconds=5))
+        assert c._checkpoint_metadata(0, timedelta(seconds=5)) == "meta_0"
+        with pytest.raises(RuntimeError, match="rank not found"):
+            c._checkpoint_metadata(7, timedelta(seconds=5))
+    finally:
+        m0.shutdown()
+        m1.shutdown()
+
+
+def test_manager_quorum_group_barrier_times_out(lighthouse):
+    ms = _manager(lighthouse, "rep", world_size=2)
+    try:
+        c = _C.ManagerClient(ms.address(), timedelta(seconds=5))
+        t0 = time.time()
+        with pytest.raises(TimeoutError):
+            c._quorum(0, 0, "", False, timedelta(milliseconds=100), 0)
+        assert time.time() - t0 < 1.0
+    finally:
+        ms.shutdown()
+
+
+def test_manager_survives_lighthouse_restart_with_retries():
+    lh = _C.LighthouseServer(bind="[::]:0", min_replicas=1, join_timeout_ms=100)
+    addr = lh.address()
+    port = int(addr.rsplit(":", 1)[1])
+    ms = _C.ManagerServer(replica_id="rep", lighthouse_addr=addr, hostname="localhost", bind="[::]:0",
+                          store_addr="s", world_size=1, heartbeat_interval=timedelta(milliseconds=50),
+                          connect_timeout=timedelta(seconds=3), quorum_retries=8)
+    try:
+        c = _C.ManagerClient(ms.address(), timedelta(seconds=5))
+        assert c._quorum(0, 0, "", False, timedelta(seconds=5), 0).quorum_id == 1
+        lh.shutdown()
+        box = {}
+
+        def ask():
+            try:
+                box["r"] = c._quorum(0, 1, "", False, timedelta(seconds=8), 0)
+            except Exception as e:  # pragma: no cover
+                box["e"] = e
+
+        t = threading.Thread(target=ask)
+        t.start()
+        time.sleep(0.5)
+        lh = _C.LighthouseServer(bind=f"[::]:{port}", min_replicas=1, join_timeout_ms=100)
+        t.join()
+        assert "r" in box, box
+        assert box["r"].replica_world_size == 1
+    finally:
+        ms.shutdown()
+        lh.shutdown()
+
+
+def test_manager_quorum_fails_fast_when_lighthouse_down():
+    lh = _C.LighthouseServer(bind="[::]:0", min_replicas=1, join_timeout_ms=100)
+    ms = _C.ManagerServer(replica_id="rep", lighthouse_addr=lh.address(), hostname="localhost", bind="[::]:0",
+                          store_addr="s", world_size=1, heartbeat_interval=timedelta(milliseconds=50),
+                          connect_timeout=timedelta(milliseconds=200), quorum_retries=0)
+    try:
+        lh.shutdown()
+        c = _C.ManagerClient(ms.address(), timedelta(seconds=5))
+        t0 = time.time()
+        with pytest.raises((RuntimeError, TimeoutError)):
+            c._quorum(0, 0, "", False, timedelta(seconds=5), 0)
+        assert time.time() - t0 < 4.0  # error is broadcast, waiters do not hang to their deadline
+    finally:
+        ms.shutdown()
+
+
+def test_dashboard_http(lighthouse):
+    c = _C.LighthouseClient(lighthouse.address(), timedelta(seconds=5))
+    c.quorum("dash", timedelta(seconds=5), address="http://nowhere:1", step=4)
+    port = lighthouse.address().rsplit(":", 1)[1]
+    index = urllib.request.urlopen(f"http://127.0.0.1:{port}/").read().decode()
+    assert "Lighthouse" in index and "/status" in index
+    status = urllib.request.urlopen(f"http://127.0.0.1:{port}/status").read().decode()
+    assert "dash" in status and "Step: 4" in status and "Heartbeats" in status
+    with pytest.raises(urllib.error.HTTPError):
+        urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{port}/replica/nobody/kill", method="POST"))

@@ -28,8 +28,13 @@ CSRC = ROOT / "csrc"
 BUILD = ROOT.parent / "build"
 EXT = sysconfig.get_config_var("EXT_SUFFIX")
 
-NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
+NVCC = os.environ.get("TFT_NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+# Use the system g++ (dynamic libstdc++, same one nvcc uses as host compiler and
+# ABI-compatible with torch). The image exports CXX=/opt/gcc/bin/g++, a toolchain
+# that links libstdc++ STATICALLY -- two C++ runtimes in one process (ours +
+# torch's) corrupt each other, so $CXX is deliberately ignored; override with
+# TFT_CXX only.
+CXX = os.environ.get("TFT_CXX") or ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++") or "g++")
 
 GENCODE = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -89,11 +94,11 @@ def build_kernels(force: bool = False, verbose: bool = False) -> Path:
 
     def cc(pair):
         src, obj = pair
-        _run([NVCC, "-c", str(src), "-o", str(obj)] + flags + _includes() + [f"-I{kdir}"])
+        _run([NVCC, "-ccbin", CXX, "-c", str(src), "-o", str(obj)] + flags + _includes() + [f"-I{kdir}"])
 
     with ThreadPoolExecutor(max_workers=min(8, len(cus))) as ex:
         list(ex.map(cc, zip(cus, objs)))
-    _run([NVCC, "-shared", "-o", str(out)] + [str(o) for o in objs] + GENCODE + ["-cudart", "static"])
+    _run([NVCC, "-ccbin", CXX, "-shared", "-o", str(out)] + [str(o) for o in objs] + GENCODE + ["-cudart", "static"])
     stamp_file.write_text(stamp)
     return out
 

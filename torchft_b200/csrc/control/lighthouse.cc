@@ -1,0 +1,250 @@
+#include "lighthouse.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <sstream>
+
+#include "manager_server.h"
+
+namespace tft {
+
+static void log_info(const std::string& msg) {
+  static const bool quiet = [] {
+    const char* e = getenv("TORCHFT_B200_LOG");
+    return !(e && (std::string(e) == "info" || std::string(e) == "debug"));
+  }();
+  if (!quiet) fprintf(stderr, "[torchft_b200 lighthouse] %s\n", msg.c_str());
+}
+
+Lighthouse::Lighthouse(LighthouseOpt opt) : opt_(std::move(opt)) {
+  start(opt_.bind, "tft-lighths");
+  tick_thread_ = std::thread([this] { tick_loop(); });
+}
+
+Lighthouse::~Lighthouse() { shutdown(); }
+
+void Lighthouse::shutdown() {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (shutdown_) return;
+    shutdown_ = true;
+  }
+  cv_.notify_all();
+  if (tick_thread_.joinable()) tick_thread_.join();
+  stop();
+}
+
+std::string Lighthouse::address() const { return "http://" + local_hostname() + ":" + std::to_string(port()); }
+
+void Lighthouse::tick_loop() {
+  std::unique_lock<std::mutex> lk(mu_);
+  while (!shutdown_) {
+    tick_locked();
+    cv_.wait_for(lk, Millis(opt_.quorum_tick_ms), [this] { return shutdown_; });
+  }
+}
+
+// Decide; when a quorum is valid: bump the id if membership changed or anyone
+// reported commit failures, publish it to all waiters, and start a fresh round.
+void Lighthouse::tick_locked() {
+  QuorumDecision d = quorum_compute(monotonic_ms(), state_, opt_);
+  if (d.reason != last_reason_) {  // change-only logging
+    log_info("Quorum status: " + d.reason);
+    last_reason_ = d.reason;
+  }
+  if (!d.participants.has_value()) return;
+  std::vector<QuorumMember>& parts = *d.participants;
+  bool commit_failures = false;
+  for (const auto& p : parts) commit_failures = commit_failures || p.commit_failures > 0;
+  if (!state_.prev_quorum.has_value() || quorum_changed(parts, state_.prev_quorum->participants)) {
+    state_.quorum_id += 1;
+    log_info("Detected quorum change, bumping quorum_id to " + std::to_string(state_.quorum_id));
+  } else if (commit_failures) {
+    state_.quorum_id += 1;
+    log_info("Detected commit failures, bumping quorum_id to " + std::to_string(state_.quorum_id));
+  }
+  Quorum q;
+  q.quorum_id = state_.quorum_id;
+  q.participants = std::move(parts);
+  q.created_ms = unix_ms();
+  state_.prev_quorum = q;
+  state_.participants.clear();
+  history_.emplace_back(++gen_, std::move(q));
+  while (history_.size() > 64) history_.pop_front();
+  cv_.notify_all();
+}
+
+uint32_t Lighthouse::handle_rpc(uint32_t method, const std::string& req, TimePoint deadline, std::string* resp) {
+  Reader r(req);
+  if (method == kLighthouseHeartbeat) {
+    std::string id = r.str();
+    std::lock_guard<std::mutex> g(mu_);
+    state_.heartbeats[id] = monotonic_ms();
+    return kStatusOk;
+  }
+  if (method != kLighthouseQuorum) {
+    *resp = "unknown lighthouse method";
+    return kStatusInvalid;
+  }
+  QuorumMember requester = QuorumMember::decode(r);
+  if (requester.replica_id.empty()) {
+    *resp = "missing requester";
+    return kStatusInvalid;
+  }
+  std::unique_lock<std::mutex> lk(mu_);
+  const int64_t now = monotonic_ms();
+  state_.heartbeats[requester.replica_id] = now;  // a quorum request is an implicit heartbeat
+  state_.participants[requester.replica_id] = ParticipantDetails{now, requester};
+  uint64_t seen = gen_;  // subscribe BEFORE the eager tick so its quorum is not missed
+  tick_locked();
+  while (true) {
+    // replay every quorum formed since we subscribed, oldest first
+    for (const auto& [g, q] : history_) {
+      if (g <= seen) continue;
+      seen = g;
+      for (const auto& p : q.participants) {
+        if (p.replica_id == requester.replica_id) {
+          Writer w;
+          q.encode(w);
+          *resp = w.take();
+          return kStatusOk;
+        }
+      }
+      // formed without us (e.g. shrink_only round): rejoin the next round
+      state_.participants[requester.replica_id] = ParticipantDetails{monotonic_ms(), requester};
+    }
+    if (shutdown_ || stopping()) {
+      *resp = "lighthouse shutting down";
+      return kStatusCancelled;
+    }
+    if (cv_.wait_until(lk, deadline) == std::cv_status::timeout && gen_ <= seen) {
+      *resp = "lighthouse quorum timed out for replica " + requester.replica_id + ": " + last_reason_;
+      return kStatusDeadline;
+    }
+  }
+}
+
+Quorum LighthouseClient::quorum(const QuorumMember& requester, Millis timeout) {
+  Writer w;
+  requester.encode(w);
+  std::string resp = rpc_.call(kLighthouseQuorum, w.data(), timeout);
+  Reader r(resp);
+  return Quorum::decode(r);
+}
+
+void LighthouseClient::heartbeat(const std::string& replica_id, Millis timeout) {
+  Writer w;
+  w.str(replica_id);
+  rpc_.call(kLighthouseHeartbeat, w.data(), timeout);
+}
+
+// ------------------------------------------------------------- dashboard
+static std::string html_escape(const std::string& s) {
+  std::string o;
+  for (char c : s) {
+    switch (c) {
+      case '&': o += "&amp;"; break;
+      case '<': o += "&lt;"; break;
+      case '>': o += "&gt;"; break;
+      case '"': o += "&quot;"; break;
+      default: o += c;
+    }
+  }
+  return o;
+}
+
+static const char* kIndexHtml = R"HTML(<!doctype html>
+<html><head><meta charset="utf-8"><title>torchft_b200 lighthouse</title>
+<style>
+body{font-family:system-ui,sans-serif;margin:2em;background:#fafafa;color:#222}
+h1{font-size:1.4em} .member{display:inline-block;border:1px solid #bbb;border-radius:6px;padding:.6em 1em;margin:.4em;background:#fff}
+.recovering{background:#ffe0b3;border-color:#e69500} .old{color:#c00;font-weight:bold}
+table{border-collapse:collapse} td,th{border:1px solid #ccc;padding:.3em .7em} button{cursor:pointer}
+</style></head><body>
+<h1>torchft_b200 Lighthouse</h1>
+<div id="status">loading…</div>
+<script>
+async function refresh(){try{const r=await fetch('/status');document.getElementById('status').innerHTML=await r.text();}catch(e){}}
+async function kill(id){if(!confirm('Kill replica '+id+'?'))return;await fetch('/replica/'+encodeURIComponent(id)+'/kill',{method:'POST'});refresh();}
+refresh();setInterval(refresh,1000);
+</script></body></html>)HTML";
+
+std::string Lighthouse::status_html() {
+  std::lock_guard<std::mutex> g(mu_);
+  const int64_t now = monotonic_ms();
+  QuorumDecision d = quorum_compute(now, state_, opt_);
+  std::ostringstream os;
+  int64_t max_step = -1, n = -1;
+  if (state_.prev_quorum) {
+    n = (int64_t)state_.prev_quorum->participants.size();
+    for (const auto& p : state_.prev_quorum->participants) max_step = std::max(max_step, p.step);
+  }
+  os << "<h2>Quorum status</h2><p>Current quorum_id: " << state_.quorum_id << "</p><p>Next quorum status: "
+     << html_escape(d.reason) << "</p>";
+  os << "<h2>Previous quorum</h2>";
+  if (state_.prev_quorum) {
+    os << "<p>Previous quorum id: " << state_.prev_quorum->quorum_id << "<br>Num participants: " << n
+       << "<br>Quorum age: " << (unix_ms() - state_.prev_quorum->created_ms) / 1000.0 << "s</p><div>";
+    for (const auto& p : state_.prev_quorum->participants) {
+      os << "<div class=\"member" << (p.step != max_step ? " recovering" : "") << "\"><b>" << html_escape(p.replica_id)
+         << "</b><br>Step: " << p.step << "<br>Manager: " << html_escape(p.address)
+         << "<br>TCPStore: " << html_escape(p.store_address) << "<br>World size: " << p.world_size
+         << "<br><button onclick=\"kill('" << html_escape(p.replica_id) << "')\">Kill</button></div>";
+    }
+    os << "</div>";
+  } else {
+    os << "<p>None</p>";
+  }
+  os << "<h2>Heartbeats</h2><table><tr><th>replica</th><th>age (s)</th></tr>";
+  for (const auto& [id, last] : state_.heartbeats) {
+    const double age = (now - last) / 1000.0;
+    os << "<tr><td>" << html_escape(id) << "</td><td" << ((now - last) >= (int64_t)opt_.heartbeat_timeout_ms ? " class=\"old\"" : "")
+       << ">" << age << "</td></tr>";
+  }
+  os << "</table>";
+  return os.str();
+}
+
+HttpResponse Lighthouse::kill_replica(const std::string& replica_id) {
+  std::string addr;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (state_.prev_quorum)
+      for (const auto& p : state_.prev_quorum->participants)
+        if (p.replica_id == replica_id) addr = p.address;
+  }
+  if (addr.empty()) return {500, "text/plain", "Something went wrong: failed to find replica"};
+  try {
+    ManagerClient c(addr, Millis(10000));
+    c.kill("killed from dashboard");
+  } catch (const std::exception& e) {
+    // the target exits before answering; a dropped connection is the expected outcome
+  }
+  return {200, "text/plain", "ok"};
+}
+
+static std::string url_decode(const std::string& s) {
+  std::string o;
+  for (size_t i = 0; i < s.size(); ++i) {
+    if (s[i] == '%' && i + 2 < s.size()) {
+      o += (char)std::stoi(s.substr(i + 1, 2), nullptr, 16);
+      i += 2;
+    } else {
+      o += s[i];
+    }
+  }
+  return o;
+}
+
+HttpResponse Lighthouse::handle_http(const HttpRequest& req) {
+  if (req.method == "GET" && (req.path == "/" || req.path == "/index.html")) return {200, "text/html; charset=utf-8", kIndexHtml};
+  if (req.method == "GET" && req.path == "/status") return {200, "text/html; charset=utf-8", status_html()};
+  const std::string pre = "/replica/", suf = "/kill";
+  if (req.method == "POST" && req.path.rfind(pre, 0) == 0 && req.path.size() > pre.size() + suf.size() &&
+      req.path.compare(req.path.size() - suf.size(), suf.size(), suf) == 0) {
+    return kill_replica(url_decode(req.path.substr(pre.size(), req.path.size() - pre.size() - suf.size())));
+  }
+  return {404, "text/plain", "not found"};
+}
+
+}  // namespace tft

@@ -176,8 +176,14 @@ int RpcClient::checkout(TimePoint deadline) {
   return connect_with_backoff(addr_, cd);
 }
 
+void RpcClient::cancel() {
+  std::lock_guard<std::mutex> g(mu_);
+  for (int fd : busy_) shutdown_fd(fd);
+}
+
 void RpcClient::checkin(int fd) {
   std::lock_guard<std::mutex> g(mu_);
+  busy_.erase(fd);
   if (idle_.size() < 4)
     idle_.push_back(fd);
   else
@@ -187,6 +193,17 @@ void RpcClient::checkin(int fd) {
 std::string RpcClient::call(uint32_t method, const std::string& payload, Millis timeout) {
   const TimePoint deadline = Clock::now() + timeout;
   int fd = checkout(deadline);
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    busy_.insert(fd);
+  }
+  auto drop = [this](int f) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      busy_.erase(f);
+    }
+    close_fd(f);
+  };
   struct {
     char magic[4];
     uint32_t method;
@@ -203,7 +220,7 @@ std::string RpcClient::call(uint32_t method, const std::string& payload, Millis 
   const TimePoint io_deadline = deadline + Millis(1000);
   if (!send_all(fd, &hdr, sizeof(hdr), io_deadline, &to) ||
       (!payload.empty() && !send_all(fd, payload.data(), payload.size(), io_deadline, &to))) {
-    close_fd(fd);
+    drop(fd);
     if (to) throw TimeoutError("rpc to " + addr_ + " timed out while sending");
     throw RpcError(kStatusUnavailable, "connection to " + addr_ + " lost while sending request");
   }
@@ -212,13 +229,13 @@ std::string RpcClient::call(uint32_t method, const std::string& payload, Millis 
     uint32_t len;
   } __attribute__((packed)) rh;
   if (!recv_all(fd, &rh, sizeof(rh), io_deadline, &to)) {
-    close_fd(fd);
+    drop(fd);
     if (to) throw TimeoutError("rpc to " + addr_ + " timed out after " + std::to_string(timeout.count()) + " ms");
     throw RpcError(kStatusUnavailable, "connection to " + addr_ + " closed before a response arrived");
   }
   std::string resp(rh.len, '\0');
   if (rh.len && !recv_all(fd, resp.data(), rh.len, io_deadline + Millis(5000), &to)) {
-    close_fd(fd);
+    drop(fd);
     throw RpcError(kStatusUnavailable, "connection to " + addr_ + " lost mid-response");
   }
   checkin(fd);

@@ -65,6 +65,8 @@ class RpcClient {
   // Throws TimeoutError on deadline (client- or server-side), RpcError otherwise.
   std::string call(uint32_t method, const std::string& payload, Millis timeout);
   const std::string& addr() const { return addr_; }
+  // Abort every in-flight call (their sockets are shut down); used at shutdown.
+  void cancel();
 
  private:
   int checkout(TimePoint deadline);
@@ -74,6 +76,7 @@ class RpcClient {
   Millis connect_timeout_;
   std::mutex mu_;
   std::vector<int> idle_;
+  std::set<int> busy_;
 };
 
 }  // namespace tft
