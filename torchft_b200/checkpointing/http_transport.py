@@ -33,6 +33,17 @@ from torchft_b200.checkpointing._serialization import streaming_load, streaming_
 from torchft_b200.checkpointing.transport import CheckpointTransport
 
 logger = logging.getLogger(__name__)
+
+
+def _advertise_host() -> str:
+    """Hostname peers should dial; falls back to loopback when the hostname does not resolve
+    (common in containers) -- on-node transports only ever talk to the same host anyway."""
+    h = socket.gethostname()
+    try:
+        socket.getaddrinfo(h, None)
+        return h
+    except OSError:
+        return "127.0.0.1"
 T = TypeVar("T")
 
 
@@ -137,7 +148,7 @@ class HTTPTransport(CheckpointTransport[T], Generic[T]):
 
     def address(self) -> str:
         port = self._server.socket.getsockname()[1]
-        return f"http://{socket.gethostname()}:{port}"
+        return f"http://{_advertise_host()}:{port}"
 
     def metadata(self) -> str:
         return f"{self.address()}/checkpoint/"

@@ -42,6 +42,17 @@ from torchft_b200.checkpointing.transport import CheckpointTransport
 from torchft_b200.ops import _native
 
 logger = logging.getLogger(__name__)
+
+
+def _advertise_host() -> str:
+    """Hostname peers should dial; falls back to loopback when the hostname does not resolve
+    (common in containers) -- on-node transports only ever talk to the same host anyway."""
+    h = socket.gethostname()
+    try:
+        socket.getaddrinfo(h, None)
+        return h
+    except OSError:
+        return "127.0.0.1"
 T = TypeVar("T")
 
 CHUNK_BYTES = 1 << 20
@@ -151,7 +162,7 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
     # ------------------------------------------------------------------ source
     def metadata(self) -> str:
         port = self._server.socket.getsockname()[1]
-        return f"http://{socket.gethostname()}:{port}"
+        return f"http://{_advertise_host()}:{port}"
 
     def send_checkpoint(self, dst_ranks: List[int], step: int, state_dict: T, timeout: timedelta) -> None:
         K = _native.load()

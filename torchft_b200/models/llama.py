@@ -163,13 +163,20 @@ class FlatParams:
 
     ALIGN = 128  # elements; keeps every view 256 B aligned
 
-    def __init__(self, module: nn.Module, grad_alloc: Optional[Callable[[int], torch.Tensor]] = None) -> None:
-        params = [p for p in module.parameters() if p.requires_grad]
-        assert params, "module has no parameters"
-        dev, dt = params[0].device, params[0].dtype
-        order = list(reversed(params))
+    def __init__(self, module: nn.Module, grad_alloc: Optional[Callable[[int], torch.Tensor]] = None,
+                 device: Optional[torch.device] = None) -> None:
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        assert named, "module has no parameters"
+        dev, dt = named[0][1].device, named[0][1].dtype
+        meta = dev.type == "meta"
+        if meta:
+            # module built on the meta device: materialise straight into the flat
+            # buffer (no transient second copy of the weights); caller initialises after.
+            assert device is not None, "pass device= when flattening a meta module"
+            dev = torch.device(device)
+        order = list(reversed(named))
         offs, total = [], 0
-        for p in order:
+        for _, p in order:
             offs.append(total)
             total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = total
@@ -177,14 +184,24 @@ class FlatParams:
         self.grad = grad_alloc(total) if grad_alloc is not None else torch.zeros(total, dtype=dt, device=dev)
         assert self.grad.numel() >= total and self.grad.dtype == dt
         self.grad = self.grad[:total]
-        self.params: List[nn.Parameter] = order
+        self.params: List[nn.Parameter] = []
         self.offsets: List[int] = offs
         with torch.no_grad():
-            for p, o in zip(order, offs):
-                v = self.param[o : o + p.numel()].view_as(p)
-                v.copy_(p.data)
-                p.data = v
-                p.grad = self.grad[o : o + p.numel()].view_as(p)
+            for (name, p), o in zip(order, offs):
+                v = self.param[o : o + p.numel()].view(p.shape)
+                if meta:
+                    q = nn.Parameter(v, requires_grad=True)
+                    owner = module
+                    *path, leaf = name.split(".")
+                    for part in path:
+                        owner = getattr(owner, part)
+                    setattr(owner, leaf, q)
+                    p = q
+                else:
+                    v.copy_(p.data)
+                    p.data = v
+                p.grad = self.grad[o : o + p.numel()].view(p.shape)
+                self.params.append(p)
 
     def buckets(self, bucket_elems: int) -> List[Tuple[int, int, List[nn.Parameter]]]:
         """Contiguous (start, end, params) buckets in gradient-production order."""

@@ -206,11 +206,22 @@ class SymmetricComm:
 
     # ------------------------------------------------------------- collectives
     def _plan(self, nbytes: int) -> Tuple[int, int]:
-        """(algo, blocks): identical on every rank for a given message size."""
-        if nbytes <= self._oneshot_max // max(1, self._world // 4):
-            blocks = max(1, min(8, nbytes // (16 * self._threads * 2) + 1))
-            return 0, blocks
-        blocks = max(4, min(self._max_blocks, nbytes // (256 << 10)))
+        """(algo, blocks): identical on every rank for a given message size.
+
+        One-shot (each rank reads everything, 2 barriers, no write-back hop) wins while
+        latency dominates; its per-block chunk is capped at 64 KB (results stay in
+        registers across the closing barrier). Two-shot moves 2(N-1)/N of the bytes and
+        uses both link directions; it gets one CTA per 64 KB up to ``max_blocks`` so
+        mid-size messages are not serialised on a handful of SMs (run1 showed 4 CTAs
+        at 1 MB cost 28 us vs 17 us for NCCL).
+        """
+        w = max(self._world, 2)
+        oneshot_max = self._oneshot_max * (4 if w == 2 else (2 if w <= 4 else 1))
+        if nbytes <= oneshot_max:
+            blocks = max(1, min(32, (nbytes + (32 << 10) - 1) // (32 << 10)))
+            if (nbytes + blocks - 1) // blocks <= (64 << 10):
+                return 0, blocks
+        blocks = max(8, min(self._max_blocks, nbytes // (64 << 10)))
         return 1, blocks
 
     def _next_flag(self) -> int:
@@ -301,7 +312,7 @@ class SymmetricComm:
             fb = b.view(-1) if b is not None else None
             for lo in range(0, fa.numel(), per):
                 n = min(per, fa.numel() - lo)
-                blocks = max(4, min(self._max_blocks, (n // 512) // 64 + 1))
+                blocks = max(4, min(148, (n // 512) // 32 + 1))  # phases A/C are local HBM passes: use the whole chip
                 K.q8_allreduce(self._tables["core"], self._status, 0, fa.data_ptr() + lo * es,
                                (fb.data_ptr() + lo * es) if fb is not None else 0, fo.data_ptr() + lo * es, n, dt,
                                scale, self._next_flag(), _CH_Q8, contribute, blocks, sp)
