@@ -280,9 +280,9 @@ def main() -> None:
         print(json.dumps(out), flush=True)
 
     trainer.shutdown()
+    if world > 1:
+        dist.barrier()  # every rank is done with the lighthouse before rank 0 stops it
     if lighthouse is not None:
-        if world > 1:
-            dist.barrier()
         lighthouse.shutdown()
     if world > 1:
         dist.destroy_process_group()

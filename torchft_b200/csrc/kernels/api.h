@@ -27,6 +27,8 @@ void q8_dequantize_launch(const void* qbuf, size_t nelem, int dtype, int world, 
                           cudaStream_t stream);
 void q8_reduce_launch(const void* const* srcs_dev, int world, int rank, size_t nelem,
                       float post_scale, void* dst, cudaStream_t stream);
+void q8_reduce_raw_launch(const void* const* srcs_dev, int nsrc, int first, size_t ngroups, size_t g_lo,
+                          size_t g_hi, float post_scale, void* dst, cudaStream_t stream);
 void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* in_a,
                          const void* in_b, void* out, size_t nelem, int dtype, float post_scale,
                          uint64_t flag, int channel, int contribute, int blocks,

@@ -210,6 +210,11 @@ PYBIND11_MODULE(_K, m) {
     q8_reduce_launch(P<const void* const>(srcs_dev), world, rank, nelem, post_scale, P<void>(dst),
                      S(stream));
   });
+  m.def("q8_reduce_raw", [](uintptr_t srcs_dev, int nsrc, int first, size_t ngroups, size_t g_lo, size_t g_hi,
+                            float post_scale, uintptr_t dst, uintptr_t stream) {
+    q8_reduce_raw_launch(P<const void* const>(srcs_dev), nsrc, first, ngroups, g_lo, g_hi, post_scale, P<void>(dst),
+                         S(stream));
+  });
   m.def(
       "q8_allreduce",
       [](const PeerTableH& pt, const Status& st, size_t off, uintptr_t in_a, uintptr_t in_b,

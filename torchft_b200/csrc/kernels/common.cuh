@@ -103,14 +103,26 @@ __device__ __forceinline__ void st_stream(void* p, const Vec16& v) {
 // latches the error into the status block; the caller must then skip the rest
 // of the collective (results are garbage; Manager discards the step).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void fence_acq_rel_sys() {
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+
 __device__ __forceinline__ bool wait_flag(const uint64_t* flag, uint64_t expected,
                                           StatusBlock* st, int peer) {
-  if (ld_acquire_sys(flag) >= expected) return true;
+  // Poll with RELAXED loads (an acquire per poll costs a system-scope fence each
+  // iteration) and acquire once at the end.
+  if (ld_relaxed_sys(flag) >= expected) {
+    fence_acq_rel_sys();
+    return true;
+  }
   const uint64_t t0 = globaltimer_ns();
   const uint64_t budget = st->timeout_ns;
   uint32_t spins = 0;
   while (true) {
-    if (ld_acquire_sys(flag) >= expected) return true;
+    if (ld_relaxed_sys(flag) >= expected) {
+      fence_acq_rel_sys();
+      return true;
+    }
     if ((++spins & 0x3ff) == 0) {
       if (st->abort) {
         st->error_rank = peer;
@@ -126,7 +138,7 @@ __device__ __forceinline__ bool wait_flag(const uint64_t* flag, uint64_t expecte
         return false;
       }
     }
-    __nanosleep(32);
+    __nanosleep(20);
   }
 }
 
@@ -135,15 +147,17 @@ __device__ __forceinline__ bool wait_flag(const uint64_t* flag, uint64_t expecte
 // Returns false (for the whole block) if any wait failed.
 __device__ __forceinline__ bool block_barrier(const PeerTable& pt, int ch, uint64_t flag,
                                               StatusBlock* st, bool release_prior_writes) {
-  __syncthreads();  // all prior work of this block (incl. peer stores) issued
+  // bar.sync makes every thread's prior (peer) stores happen-before thread t's
+  // release store; st.release.sys is cumulative, so no separate fence.sc.sys is
+  // needed (run2: the explicit __threadfence_system() here serialised chip-wide
+  // and cost ~0.8 us per CTA per barrier).
+  __syncthreads();
   const int t = threadIdx.x;
   int ok = 1;
-  if (t < pt.world) {
-    if (release_prior_writes) __threadfence_system();
-    if (t != pt.rank) {
-      st_release_sys(&pt.pads[t]->sig[ch][blockIdx.x][pt.rank], flag);
-      ok = wait_flag(&pt.pads[pt.rank]->sig[ch][blockIdx.x][t], flag, st, t) ? 1 : 0;
-    }
+  if (t < pt.world && t != pt.rank) {
+    (void)release_prior_writes;
+    st_release_sys(&pt.pads[t]->sig[ch][blockIdx.x][pt.rank], flag);
+    ok = wait_flag(&pt.pads[pt.rank]->sig[ch][blockIdx.x][t], flag, st, t) ? 1 : 0;
   }
   return __syncthreads_and(ok) != 0;
 }

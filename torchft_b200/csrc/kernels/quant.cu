@@ -388,6 +388,15 @@ void q8_dequantize_launch(const void* qbuf, size_t nelem, int dtype, int world, 
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 
+void q8_reduce_raw_launch(const void* const* srcs_dev, int nsrc, int first, size_t ngroups, size_t g_lo,
+                          size_t g_hi, float post_scale, void* dst, cudaStream_t stream) {
+  if (g_hi <= g_lo) return;
+  const int grid = q8_grid(g_hi - g_lo, 1184);
+  q8_reduce_kernel<<<grid, 512, 0, stream>>>((const char* const*)srcs_dev, nsrc, first, ngroups, g_lo, g_hi,
+                                             post_scale, (char*)dst);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
 void q8_reduce_launch(const void* const* srcs_dev, int world, int rank, size_t nelem,
                       float post_scale, void* dst, cudaStream_t stream) {
   const size_t ng = q8_ngroups(nelem, world);

@@ -346,6 +346,36 @@ class Manager:
             return pg.allreduce_q8(tensor, tensor, None, scale=scale, contribute=participating)  # type: ignore[attr-defined]
         return fused(tensor, op=ops[reduce_op], scale=scale, contribute=participating)
 
+    def supports_fused_delta(self) -> bool:
+        """True when ``allreduce_delta`` runs as ONE fused kernel (ProcessGroupB200)."""
+        return hasattr(self._pg, "allreduce_q8") and torch.cuda.is_available()
+
+    @torch.profiler.record_function("torchft::manager::allreduce_delta")
+    def allreduce_delta(self, out: torch.Tensor, a: torch.Tensor, b: torch.Tensor, should_quantize: bool = True) -> Work:
+        """``out = AVG over replicas of (a - b)`` -- DiLoCo's pseudo-gradient reduction.
+
+        On ProcessGroupB200 with ``should_quantize`` the subtraction, fp8 quantisation,
+        exchange, fp32 reduction and dequantisation are one kernel; elsewhere this is
+        ``torch.sub`` followed by :meth:`allreduce`. ``out`` may alias ``a``. Same
+        error-latching contract as :meth:`allreduce`.
+        """
+        if self.errored():
+            return DummyWork(out)
+        self.wait_quorum()
+        n = self.num_participants()
+        participating = self.is_participating()
+        try:
+            pg = self._pg
+            if should_quantize and self.supports_fused_delta() and all(pg._native_ok(t) for t in (out, a, b)):  # type: ignore[attr-defined]
+                work = pg.allreduce_q8(out, a, b, scale=1.0 / max(n, 1), contribute=participating)  # type: ignore[attr-defined]
+                return _ManagedWork(self, work, out)
+        except Exception as e:  # noqa: BLE001
+            self._logger.exception(f"got exception in allreduce_delta -- skipping remaining: {e}")
+            self.report_error(e)
+            return DummyWork(out)
+        torch.sub(a, b, out=out)
+        return self.allreduce(out, should_quantize=should_quantize)
+
     def report_error(self, e: Exception) -> None:
         """Latch an error: the current step will not commit and the group reconfigures next step."""
         self._errored = ExceptionWithTraceback(e)
