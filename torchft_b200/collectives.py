@@ -73,17 +73,75 @@ def _check(tensors: List[torch.Tensor], op: ReduceOp) -> None:
         raise ValueError("quantized collectives need CUDA tensors")
 
 
+def _rank_of(pg: Any) -> int:
+    r = getattr(pg, "rank", None)
+    if callable(r):
+        try:
+            return int(r())
+        except Exception:  # noqa: BLE001
+            pass
+    inner = getattr(pg, "_rank", None)
+    if isinstance(inner, int):
+        return inner
+    return dist.get_rank(pg)
+
+
+class _SlicePlan:
+    """Per-tensor slicing of a flat message into ``world`` equal slices, each quantised as a
+    standalone Q8G chunk (fp32 scale per 512 elements + e4m3 payload) so that chunk ``r`` of every
+    tensor can be concatenated into ONE contiguous all-to-all segment for rank ``r``."""
+
+    def __init__(self, tensors: List[torch.Tensor], world: int, slice_elems: Optional[List[int]] = None) -> None:
+        self.world = world
+        self.slice_elems: List[int] = []
+        self.groups: List[int] = []
+        self.offsets: List[int] = []
+        off = 0
+        for i, t in enumerate(tensors):
+            if slice_elems is not None:
+                se = slice_elems[i]
+            else:
+                se = (t.numel() + world - 1) // world
+                se = (se + 7) // 8 * 8  # slice starts stay 16 B aligned for every dtype we support
+            g = (se + Q.GROUP - 1) // Q.GROUP
+            self.slice_elems.append(se)
+            self.groups.append(g)
+            self.offsets.append(off)
+            off += ((g * 4 + 15) // 16 * 16) + g * Q.GROUP
+        self.chunk_bytes = (off + 15) // 16 * 16
+
+
+def _quantize_slices(tensors: List[torch.Tensor], plan: _SlicePlan, send: torch.Tensor) -> None:
+    K = _native.load()
+    sp = _native.stream_ptr()
+    for t, se, g, off in zip(tensors, plan.slice_elems, plan.groups, plan.offsets):
+        es, n = t.element_size(), t.numel()
+        for r in range(plan.world):
+            valid = max(0, min(se, n - r * se))
+            src = t.data_ptr() + r * se * es if valid > 0 else t.data_ptr()
+            K.q8_quantize_raw(src, 0, valid, g, _native.dtype_code(t), send[r].data_ptr() + off, sp)
+
+
+def _reduce_slices(tensors: List[torch.Tensor], plan: _SlicePlan, recv: torch.Tensor, out_chunk: torch.Tensor,
+                   rank: int, post_scale: float) -> None:
+    K = _native.load()
+    sp = _native.stream_ptr()
+    for g, off in zip(plan.groups, plan.offsets):
+        ptrs = torch.tensor([recv[p].data_ptr() + off for p in range(plan.world)], dtype=torch.int64, device=recv.device)
+        K.q8_reduce_raw(ptrs.data_ptr(), plan.world, rank, g, 0, g, post_scale, out_chunk.data_ptr() + off, sp)
+
+
 def allreduce_quantized(tensors: List[torch.Tensor], opts: AllreduceOptions | ReduceOp, process_group: dist.ProcessGroup,
                         sync_stream: Optional[torch.cuda.Stream] = None) -> Work:
     """In-place fp8 all-reduce of ``tensors`` (SUM or AVG).
 
-    quantize -> all-to-all of row slices -> fp32 reduce + requantize of the local slice ->
+    quantize -> all-to-all of per-rank slices -> fp32 reduce + requantize of the local slice ->
     all-gather -> dequantize, all enqueued on ``sync_stream`` (a side stream by default).
     Expected mean relative error <= 0.04 (reference tolerance, collectives_test.py:186).
     """
     op = _op_of(opts)
     _check(tensors, op)
-    world, rank = process_group.size(), process_group.rank() if hasattr(process_group, "rank") else dist.get_rank(process_group)
+    world = process_group.size()
     fused = getattr(process_group, "allreduce_q8", None)
     if fused is not None:  # ProcessGroupB200: one kernel per tensor, no NCCL
         scale = 1.0 / world if op == ReduceOp.AVG else 1.0
@@ -91,29 +149,33 @@ def allreduce_quantized(tensors: List[torch.Tensor], opts: AllreduceOptions | Re
         for w in works[:-1]:
             w.wait()
         return works[-1]
+    rank = _rank_of(process_group)
+    K = _native.load()
     stream = sync_stream if sync_stream is not None else torch.cuda.Stream()
     stream.wait_stream(torch.cuda.current_stream())
-    contig = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+    contig = [t if (t.is_contiguous() and t.data_ptr() % 16 == 0) else t.contiguous() for t in tensors]
     with torch.cuda.stream(stream):
-        qbuf = Q.fused_quantize_into_fp8(contig, world)
-        recv = torch.empty((world, qbuf.numel()), dtype=torch.uint8, device=qbuf.device)
-        # Q8G keeps each rank's groups contiguous per tensor but tensors are laid out back to
-        # back, so ship the whole buffer to every peer (all-gather) and let each rank reduce
-        # only its own group range: same bytes on the wire as all-to-all + all-gather of slices
-        # for world <= 2 and simpler bookkeeping; for larger worlds prefer ProcessGroupB200.
-        ag = AllgatherOptions()
-        process_group.allgather([list(recv.unbind(0))], [qbuf], ag).wait()
-        bufs = list(recv.unbind(0))
-        Q.fused_reduce_fp8(contig, bufs, world, rank, op)
-        # gather every rank's reduced slice
-        red = torch.empty_like(recv)
-        process_group.allgather([list(red.unbind(0))], [bufs[rank]], ag).wait()
-        final = Q.merge_reduced_slices(contig, list(red.unbind(0)), world)
-        Q.fused_dequantize_from_fp8(contig, final, world)
+        plan = _SlicePlan(contig, world)
+        dev = contig[0].device
+        send = torch.zeros((world, plan.chunk_bytes), dtype=torch.uint8, device=dev)
+        _quantize_slices(contig, plan, send)
+        recv = torch.empty_like(send)
+        process_group.alltoall_base(recv.view(-1), send.view(-1), [], [], AllToAllOptions()).wait()
+        mine = torch.zeros(plan.chunk_bytes, dtype=torch.uint8, device=dev)
+        _reduce_slices(contig, plan, recv, mine, rank, 1.0 / world if op == ReduceOp.AVG else 1.0)
+        gathered = torch.empty((world, plan.chunk_bytes), dtype=torch.uint8, device=dev)
+        process_group.allgather([list(gathered.unbind(0))], [mine], AllgatherOptions()).wait()
+        sp = _native.stream_ptr()
+        for t, se, g, off in zip(contig, plan.slice_elems, plan.groups, plan.offsets):
+            es, n = t.element_size(), t.numel()
+            for r in range(world):
+                valid = max(0, min(se, n - r * se))
+                if valid > 0:
+                    K.q8_dequantize_raw(gathered[r].data_ptr() + off, g, t.data_ptr() + r * se * es, valid,
+                                        _native.dtype_code(t), sp)
         for t, c in zip(tensors, contig):
             if t.data_ptr() != c.data_ptr():
                 t.copy_(c)
-        for t in tensors:
             t.record_stream(stream)
     return _StreamWork(stream, tensors)
 
@@ -121,27 +183,52 @@ def allreduce_quantized(tensors: List[torch.Tensor], opts: AllreduceOptions | Re
 def reduce_scatter_quantized(output: torch.Tensor, inputs: List[torch.Tensor], opts: ReduceScatterOptions | ReduceOp,
                              process_group: dist.ProcessGroup, sync_stream: Optional[torch.cuda.Stream] = None) -> Work:
     """fp8 reduce-scatter: ``output`` receives this rank's row-slice of every (row-padded) input,
-    concatenated (layout of :func:`allocate_reduce_scatter_output`)."""
+    concatenated (layout of :func:`allocate_reduce_scatter_output`): quantize -> all-to-all ->
+    fp32 reduce -> dequantize own slice. No all-gather."""
     op = _op_of(opts)
     _check(inputs, op)
     world = process_group.size()
-    rank = process_group.rank() if hasattr(process_group, "rank") else dist.get_rank(process_group)
+    rank = _rank_of(process_group)
+    K = _native.load()
     stream = sync_stream if sync_stream is not None else torch.cuda.Stream()
     stream.wait_stream(torch.cuda.current_stream())
     padded = get_padded_sizes(inputs, world)
     with torch.cuda.stream(stream):
-        # pad rows so every rank owns an equal slice, reduce in fp8, keep only our slice
-        work_tensors = []
+        work_tensors, slices = [], []
         for t, ps in zip(inputs, padded):
+            rows = t.shape[0] if t.dim() else 1
             p = torch.zeros(ps, dtype=t.dtype, device=t.device)
-            p.view(ps[0], -1)[: (t.shape[0] if t.dim() else 1)].copy_(t.reshape(t.shape[0] if t.dim() else 1, -1))
+            p.view(ps[0], -1)[:rows].copy_(t.reshape(rows, -1))
             work_tensors.append(p)
-        allreduce_quantized(work_tensors, op, process_group, stream).wait()
-        off = 0
-        for p in work_tensors:
-            rows = p.shape[0] // world
-            sl = p[rank * rows : (rank + 1) * rows].reshape(-1)
-            output[off : off + sl.numel()].copy_(sl)
-            off += sl.numel()
+            slices.append(p.numel() // world)
+        es = work_tensors[0].element_size()
+        if any((s * es) % 16 for s in slices):
+            # rows too narrow for aligned slices: reduce everything, keep our rows
+            allreduce_quantized(work_tensors, op, process_group, stream).wait()
+            off = 0
+            for p, s in zip(work_tensors, slices):
+                output[off : off + s].copy_(p.view(-1)[rank * s : (rank + 1) * s])
+                off += s
+        else:
+            plan = _SlicePlan(work_tensors, world, slices)
+            dev = work_tensors[0].device
+            send = torch.zeros((world, plan.chunk_bytes), dtype=torch.uint8, device=dev)
+            _quantize_slices(work_tensors, plan, send)
+            recv = torch.empty_like(send)
+            process_group.alltoall_base(recv.view(-1), send.view(-1), [], [], AllToAllOptions()).wait()
+            mine = torch.zeros(plan.chunk_bytes, dtype=torch.uint8, device=dev)
+            _reduce_slices(work_tensors, plan, recv, mine, rank, 1.0 / world if op == ReduceOp.AVG else 1.0)
+            sp = _native.stream_ptr()
+            off = 0
+            aligned_out = output.data_ptr() % 16 == 0 and output.is_contiguous()
+            for p, s, g, coff in zip(work_tensors, plan.slice_elems, plan.groups, plan.offsets):
+                dst = output[off : off + s]
+                if aligned_out and (off * es) % 16 == 0:
+                    K.q8_dequantize_raw(mine.data_ptr() + coff, g, dst.data_ptr(), s, _native.dtype_code(p), sp)
+                else:
+                    tmp = torch.empty(s, dtype=p.dtype, device=dev)
+                    K.q8_dequantize_raw(mine.data_ptr() + coff, g, tmp.data_ptr(), s, _native.dtype_code(p), sp)
+                    dst.copy_(tmp)
+                off += s
         output.record_stream(stream)
     return _StreamWork(stream, output)

@@ -27,6 +27,10 @@ void q8_dequantize_launch(const void* qbuf, size_t nelem, int dtype, int world, 
                           cudaStream_t stream);
 void q8_reduce_launch(const void* const* srcs_dev, int world, int rank, size_t nelem,
                       float post_scale, void* dst, cudaStream_t stream);
+void q8_quantize_raw_launch(const void* a, const void* b, size_t nelem, size_t ngroups, int dtype, void* qbuf,
+                            cudaStream_t stream);
+void q8_dequantize_raw_launch(const void* qbuf, size_t ngroups, void* out, size_t nelem, int dtype,
+                              cudaStream_t stream);
 void q8_reduce_raw_launch(const void* const* srcs_dev, int nsrc, int first, size_t ngroups, size_t g_lo,
                           size_t g_hi, float post_scale, void* dst, cudaStream_t stream);
 void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* in_a,

@@ -210,6 +210,14 @@ PYBIND11_MODULE(_K, m) {
     q8_reduce_launch(P<const void* const>(srcs_dev), world, rank, nelem, post_scale, P<void>(dst),
                      S(stream));
   });
+  m.def("q8_quantize_raw", [](uintptr_t a, uintptr_t b, size_t nelem, size_t ngroups, int dtype, uintptr_t qbuf,
+                              uintptr_t stream) {
+    q8_quantize_raw_launch(P<void>(a), P<void>(b), nelem, ngroups, dtype, P<void>(qbuf), S(stream));
+  });
+  m.def("q8_dequantize_raw", [](uintptr_t qbuf, size_t ngroups, uintptr_t out, size_t nelem, int dtype,
+                                uintptr_t stream) {
+    q8_dequantize_raw_launch(P<void>(qbuf), ngroups, P<void>(out), nelem, dtype, S(stream));
+  });
   m.def("q8_reduce_raw", [](uintptr_t srcs_dev, int nsrc, int first, size_t ngroups, size_t g_lo, size_t g_hi,
                             float post_scale, uintptr_t dst, uintptr_t stream) {
     q8_reduce_raw_launch(P<const void* const>(srcs_dev), nsrc, first, ngroups, g_lo, g_hi, post_scale, P<void>(dst),

@@ -388,6 +388,41 @@ void q8_dequantize_launch(const void* qbuf, size_t nelem, int dtype, int world, 
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 
+void q8_quantize_raw_launch(const void* a, const void* b, size_t nelem, size_t ngroups, int dtype, void* qbuf,
+                            cudaStream_t stream) {
+  if (ngroups == 0) return;
+  const int grid = q8_grid(ngroups, 1184);
+  switch (dtype) {
+    case kF32:
+      q8_quantize_kernel<float><<<grid, 512, 0, stream>>>((const float*)a, (const float*)b, nelem, ngroups, (char*)qbuf);
+      break;
+    case kBF16:
+      q8_quantize_kernel<__nv_bfloat16><<<grid, 512, 0, stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                                  nelem, ngroups, (char*)qbuf);
+      break;
+    case kF16:
+      q8_quantize_kernel<__half><<<grid, 512, 0, stream>>>((const __half*)a, (const __half*)b, nelem, ngroups, (char*)qbuf);
+      break;
+    default: throw std::runtime_error("q8_quantize: unsupported dtype");
+  }
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void q8_dequantize_raw_launch(const void* qbuf, size_t ngroups, void* out, size_t nelem, int dtype,
+                              cudaStream_t stream) {
+  if (ngroups == 0 || nelem == 0) return;
+  const int grid = q8_grid(ngroups, 1184);
+  switch (dtype) {
+    case kF32: q8_dequantize_kernel<float><<<grid, 512, 0, stream>>>((const char*)qbuf, ngroups, (float*)out, nelem); break;
+    case kBF16:
+      q8_dequantize_kernel<__nv_bfloat16><<<grid, 512, 0, stream>>>((const char*)qbuf, ngroups, (__nv_bfloat16*)out, nelem);
+      break;
+    case kF16: q8_dequantize_kernel<__half><<<grid, 512, 0, stream>>>((const char*)qbuf, ngroups, (__half*)out, nelem); break;
+    default: throw std::runtime_error("q8_dequantize: unsupported dtype");
+  }
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
 void q8_reduce_raw_launch(const void* const* srcs_dev, int nsrc, int first, size_t ngroups, size_t g_lo,
                           size_t g_hi, float post_scale, void* dst, cudaStream_t stream) {
   if (g_hi <= g_lo) return;

@@ -115,20 +115,3 @@ def fused_reduce_fp8(inputs: List[torch.Tensor], all_buffers: List[torch.Tensor]
         ptrs = torch.tensor([b.data_ptr() + o for b in all_buffers], dtype=torch.int64, device=dev)
         K.q8_reduce(ptrs.data_ptr(), world_size, rank, t.numel(), post, all_buffers[rank].data_ptr() + o, sp)
 
-
-def merge_reduced_slices(inputs: List[torch.Tensor], per_rank: List[torch.Tensor], world_size: int) -> torch.Tensor:
-    """Assemble one full Q8G buffer from buffers in which rank ``r``'s group range holds the
-    reduced result (the "all-gather" step of the generic quantised all-reduce)."""
-    K = _native.load()
-    offs, total = _layout(inputs, world_size)
-    out = torch.empty(total, dtype=torch.uint8, device=inputs[0].device)
-    for t, o in zip(inputs, offs):
-        ng = K.q8_ngroups(t.numel(), world_size)
-        per = ng // world_size
-        poff = (ng * 4 + 15) // 16 * 16
-        for r in range(world_size):
-            src = per_rank[r]
-            out[o + r * per * 4 : o + (r + 1) * per * 4].copy_(src[o + r * per * 4 : o + (r + 1) * per * 4])
-            lo, hi = o + poff + r * per * GROUP, o + poff + (r + 1) * per * GROUP
-            out[lo:hi].copy_(src[lo:hi])
-    return out
