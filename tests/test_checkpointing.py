@@ -1,0 +1,176 @@
+"""Checkpoint transports: generic multi-node recovery scenario (threads + barriers) run against
+HTTP (full and chunked) and PG (gloo) transports; RWLock semantics; step mismatch and timeouts."""
+
+import copy
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from datetime import timedelta
+
+import pytest
+import torch
+from torch.distributed import TCPStore
+
+from torchft_b200.checkpointing import HTTPTransport, PGTransport
+from torchft_b200.checkpointing._rwlock import RWLock
+from torchft_b200.process_group import ProcessGroupGloo
+
+
+def make_state(seed: int):
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "model": {"w": torch.rand(5, 3, generator=g), "b": torch.rand(3, generator=g).to(torch.bfloat16), "empty": torch.zeros(0)},
+        "step": seed,
+        "name": f"ckpt{seed}",
+        "nested": [torch.arange(4), {"x": 1.5}],
+    }
+
+
+def assert_state_equal(a, b):
+    assert a["step"] == b["step"] and a["name"] == b["name"] and a["nested"][1] == b["nested"][1]
+    for k in a["model"]:
+        assert torch.equal(a["model"][k], b["model"][k]), k
+    assert torch.equal(a["nested"][0], b["nested"][0])
+
+
+def run_multi_recovery(make_transport, world=3, timeout=timedelta(seconds=10)):
+    """rank 0 serves steps 1 and 2; ranks 1..n-1 fetch; then a fetch after disallow must fail/timeout."""
+    transports = [make_transport(r, world) for r in range(world)]
+    barrier = threading.Barrier(world)
+    results = {}
+
+    def node(rank):
+        tr = transports[rank]
+        for step in (1, 2):
+            if rank == 0:
+                # PG transports block here until every receiver has pulled its copy; HTTP returns at once
+                tr.send_checkpoint(list(range(1, world)), step, make_state(step), timeout)
+                barrier.wait()
+                tr.disallow_checkpoint()
+            else:
+                # may start before the sender is ready: HTTP GETs park on the read lock, PG recvs on the wire
+                got = tr.recv_checkpoint(0, transports[0].metadata(), step, timeout)
+                results[(rank, step)] = copy.deepcopy(got)  # in-place receivers reuse the same tensors
+                barrier.wait()
+            barrier.wait()  # nobody starts the next step before the sender closed this one
+        return True
+
+    with ThreadPoolExecutor(max_workers=world) as ex:
+        assert all(ex.map(node, range(world)))
+    for r in range(1, world):
+        for step in (1, 2):
+            assert_state_equal(results[(r, step)], make_state(step))
+    return transports
+
+
+@pytest.mark.parametrize("num_chunks", [0, 3])
+def test_http_transport_recovery(num_chunks):
+    trs = run_multi_recovery(lambda r, w: HTTPTransport(timedelta(seconds=10), num_chunks=num_chunks))
+    try:
+        # after disallow: requests block until the (short) timeout -> error, never stale data
+        trs[1]._timeout = timedelta(seconds=1)
+        trs[0]._lock.timeout = 0.3
+        with pytest.raises((TimeoutError, RuntimeError)):
+            trs[1].recv_checkpoint(0, trs[0].metadata(), 2, timedelta(seconds=2))
+    finally:
+        for t in trs:
+            t.shutdown()
+
+
+def test_http_transport_step_mismatch():
+    src = HTTPTransport(timedelta(seconds=5))
+    dst = HTTPTransport(timedelta(seconds=5))
+    try:
+        src.send_checkpoint([1], 7, make_state(7), timedelta(seconds=5))
+        with pytest.raises(RuntimeError, match="invalid checkpoint requested"):
+            dst.recv_checkpoint(0, src.metadata(), 8, timedelta(seconds=5))
+        assert_state_equal(dst.recv_checkpoint(0, src.metadata(), 7, timedelta(seconds=5)), make_state(7))
+    finally:
+        src.shutdown()
+        dst.shutdown()
+
+
+def test_pg_transport_recovery_and_inplace():
+    store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
+    world = 3
+    pgs = [ProcessGroupGloo(timeout=timedelta(seconds=10)) for _ in range(world)]
+
+    def cfg(r):
+        pgs[r].configure(f"127.0.0.1:{store.port}/pgt/0", f"r{r}", r, world)
+
+    with ThreadPoolExecutor(max_workers=world) as ex:
+        list(ex.map(cfg, range(world)))
+    inplace_targets = {r: make_state(99) for r in range(world)}
+    trs = run_multi_recovery(lambda r, w: PGTransport(pgs[r], timedelta(seconds=10), torch.device("cpu"),
+                                                      state_dict=(lambda rr=r: inplace_targets[rr]) if r == 2 else None),
+                             world=world)
+    # rank 2 received in place: its pre-existing tensors now hold step-2 values
+    assert torch.equal(inplace_targets[2]["model"]["w"], make_state(2)["model"]["w"])
+    for pg in pgs:
+        pg.shutdown()
+
+
+def test_pg_transport_step_mismatch():
+    store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
+    pgs = [ProcessGroupGloo(timeout=timedelta(seconds=5)) for _ in range(2)]
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        list(ex.map(lambda r: pgs[r].configure(f"127.0.0.1:{store.port}/pgm/0", f"r{r}", r, 2), range(2)))
+    trs = [PGTransport(pgs[r], timedelta(seconds=5), torch.device("cpu")) for r in range(2)]
+
+    def send():
+        trs[0].send_checkpoint([1], 3, make_state(3), timedelta(seconds=5))
+
+    t = threading.Thread(target=send)
+    t.start()
+    with pytest.raises(RuntimeError, match="step mismatch"):
+        trs[1].recv_checkpoint(0, "", 4, timedelta(seconds=5))
+    t.join(timeout=10)
+    for pg in pgs:
+        pg.shutdown()
+
+
+def test_rwlock_readers_writer_and_timeouts():
+    lock = RWLock(timeout=0.2)
+    with lock.r_lock():
+        with lock.r_lock():  # many readers
+            assert lock.w_locked()
+            with pytest.raises(TimeoutError):
+                lock.w_acquire()
+    assert not lock.w_locked()
+    lock.w_acquire()
+    assert lock.w_locked()
+    with pytest.raises(TimeoutError):
+        lock.r_acquire()
+    # release from ANOTHER thread is allowed
+    t = threading.Thread(target=lock.w_release)
+    t.start()
+    t.join()
+    with lock.r_lock():
+        pass
+
+
+def test_rwlock_writer_preference():
+    lock = RWLock(timeout=2.0)
+    lock.r_acquire()
+    got = []
+
+    def writer():
+        lock.w_acquire()
+        got.append("w")
+        lock.w_release()
+
+    def late_reader():
+        time.sleep(0.1)
+        lock.r_acquire()
+        got.append("r")
+        lock.r_release()
+
+    tw, tr = threading.Thread(target=writer), threading.Thread(target=late_reader)
+    tw.start()
+    tr.start()
+    time.sleep(0.3)
+    assert got == []  # writer waits for the first reader; late reader queues BEHIND the writer
+    lock.r_release()
+    tw.join()
+    tr.join()
+    assert got == ["w", "r"]

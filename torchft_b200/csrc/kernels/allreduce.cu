@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(512, 1) allreduce_twoshot_kernel(ARArgs a) {
                        !a.contribute);
     }
   }
-  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/true)) return;
+  const bool staged = (a.user_in != nullptr || !a.contribute);
+  // peer data read below was produced before the peers' kernels started (or released by their
+  // fence when staged) and is only touched with L1-bypassing loads: no acquire fence needed
+  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/staged, /*acquire=*/false)) return;
 
   // ---- phase 1+2: reduce my slice from all peers, push result to all peers ----
   {
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(512, 1) allreduce_twoshot_kernel(ARArgs a) {
       }
     }
   }
-  if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/true)) return;
+  if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/true, /*acquire=*/a.user_out != nullptr)) return;
 
   // ---- phase 3: symmetric segment -> user tensor ----
   if (a.user_out != nullptr) {
@@ -167,7 +170,9 @@ __global__ void __launch_bounds__(512, 1) allreduce_oneshot_kernel(ARArgs a) {
     if (lo < hi)
       copy_region<T>(mine, reinterpret_cast<const T*>(a.user_in), lo, hi, a.nelem, !a.contribute);
   }
-  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, true)) return;
+  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/(a.user_in != nullptr || !a.contribute),
+                     /*acquire=*/false))
+    return;
 
   const T* src[W];
 #pragma unroll
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(512, 1) allreduce_oneshot_kernel(ARArgs a) {
         for (size_t k = e; k < a.nelem; ++k) out[k] = T(acc[k - e]);
       }
     }
-    block_barrier(a.pt, a.channel, a.flag + 2, a.st, false);
+    block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/false, /*acquire=*/false);
   } else {
     // In-place in staging: host guarantees chunk <= blockDim.x * kMaxRounds.
     constexpr int kMaxRounds = 8;
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(512, 1) allreduce_oneshot_kernel(ARArgs a) {
         res[r] = Pack<T>::pack(acc);
       }
     }
-    if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, false)) return;
+    if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/false, /*acquire=*/false)) return;
 #pragma unroll
     for (int r = 0; r < kMaxRounds; ++r) {
       const size_t v = lo + threadIdx.x + (size_t)r * blockDim.x;

@@ -106,23 +106,22 @@ __device__ __forceinline__ void st_stream(void* p, const Vec16& v) {
 __device__ __forceinline__ void fence_acq_rel_sys() {
   asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
+// Poll a peer flag with RELAXED loads (no fence per poll). Returns false on
+// timeout/abort, or immediately when an earlier collective already latched an
+// error (so a dead peer costs ONE timeout, not one per queued kernel).
 __device__ __forceinline__ bool wait_flag(const uint64_t* flag, uint64_t expected,
                                           StatusBlock* st, int peer) {
-  // Poll with RELAXED loads (an acquire per poll costs a system-scope fence each
-  // iteration) and acquire once at the end.
-  if (ld_relaxed_sys(flag) >= expected) {
-    fence_acq_rel_sys();
-    return true;
-  }
+  if (ld_relaxed_sys(flag) >= expected) return true;
+  if (st->error != kOk) return false;
   const uint64_t t0 = globaltimer_ns();
   const uint64_t budget = st->timeout_ns;
   uint32_t spins = 0;
   while (true) {
-    if (ld_relaxed_sys(flag) >= expected) {
-      fence_acq_rel_sys();
-      return true;
-    }
+    if (ld_relaxed_sys(flag) >= expected) return true;
     if ((++spins & 0x3ff) == 0) {
       if (st->abort) {
         st->error_rank = peer;
@@ -143,23 +142,38 @@ __device__ __forceinline__ bool wait_flag(const uint64_t* flag, uint64_t expecte
 }
 
 // Block-granular barrier across ranks on channel `ch`: block b of every rank
-// rendezvous with block b of every peer. Threads 0..world-1 each own one peer.
-// Returns false (for the whole block) if any wait failed.
+// rendezvous with block b of every peer; threads 0..world-1 each own one peer.
+//
+// System-scope fences (MEMBAR.SYS) are the expensive part: run2/run3 showed
+// their cost growing ~1 us per participating CTA, i.e. they serialise chip-wide.
+// So the barrier issues AT MOST ONE release fence and ONE acquire fence per CTA
+// (by thread 0, made cumulative over the CTA by bar.sync), independent of the
+// world size, and the caller says which side it actually needs:
+//   release: this CTA wrote data (to its own or to peer memory) that peers read
+//            after the barrier. Not needed when the data was produced by an
+//            earlier kernel (kernel boundaries already order it).
+//   acquire: this CTA reads peer-written data after the barrier within this
+//            kernel. All such loads use L1-bypassing accesses, so the fence only
+//            pins the ordering required by the PTX memory model.
 __device__ __forceinline__ bool block_barrier(const PeerTable& pt, int ch, uint64_t flag,
-                                              StatusBlock* st, bool release_prior_writes) {
-  // bar.sync makes every thread's prior (peer) stores happen-before thread t's
-  // release store; st.release.sys is cumulative, so no separate fence.sc.sys is
-  // needed (run2: the explicit __threadfence_system() here serialised chip-wide
-  // and cost ~0.8 us per CTA per barrier).
+                                              StatusBlock* st, bool release, bool acquire = true) {
   __syncthreads();
   const int t = threadIdx.x;
+  if (release) {
+    if (t == 0) fence_acq_rel_sys();
+    __syncthreads();
+  }
   int ok = 1;
   if (t < pt.world && t != pt.rank) {
-    (void)release_prior_writes;
-    st_release_sys(&pt.pads[t]->sig[ch][blockIdx.x][pt.rank], flag);
+    st_relaxed_sys(&pt.pads[t]->sig[ch][blockIdx.x][pt.rank], flag);
     ok = wait_flag(&pt.pads[pt.rank]->sig[ch][blockIdx.x][t], flag, st, t) ? 1 : 0;
   }
-  return __syncthreads_and(ok) != 0;
+  ok = __syncthreads_and(ok);
+  if (acquire) {
+    if (t == 0) fence_acq_rel_sys();
+    __syncthreads();
+  }
+  return ok != 0;
 }
 
 // ---------------------------------------------------------------------------

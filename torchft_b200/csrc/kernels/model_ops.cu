@@ -289,35 +289,42 @@ struct AdamArgs {
   const int* gate;
 };
 
-__global__ void __launch_bounds__(512) adamw_kernel(AdamArgs a) {
+__global__ void __launch_bounds__(512, 2) adamw_kernel(AdamArgs a) {
   if (a.gate != nullptr && *a.gate == 0) return;
   const size_t nvec = a.n / 8;
   const float step_size = a.lr / a.bc1;
   const float inv_bc2_sqrt = rsqrtf(a.bc2);
+  const float decay = 1.f - a.lr * a.wd;
   for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec;
        v += (size_t)gridDim.x * blockDim.x) {
-    float g[8], o[8];
-    P8::unpack(ld_stream(a.g + v * 8), g);
+    // all 7 x 16 B loads in flight before any use (28 B/param streams through once)
+    const Vec16 gv = ld_stream(a.g + v * 8);
+    const Vec16 w0 = ld_stream(a.master + v * 8), w1 = ld_stream(a.master + v * 8 + 4);
+    const Vec16 m0 = ld_stream(a.m + v * 8), m1 = ld_stream(a.m + v * 8 + 4);
+    const Vec16 v0 = ld_stream(a.v + v * 8), v1 = ld_stream(a.v + v * 8 + 4);
+    float g[8], w[8], m[8], vv[8];
+    P8::unpack(gv, g);
+    Pack<float>::unpack(w0, w);
+    Pack<float>::unpack(w1, w + 4);
+    Pack<float>::unpack(m0, m);
+    Pack<float>::unpack(m1, m + 4);
+    Pack<float>::unpack(v0, vv);
+    Pack<float>::unpack(v1, vv + 4);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float w[4], m[4], vv[4];
-      Pack<float>::unpack(ld_stream(a.master + v * 8 + 4 * h), w);
-      Pack<float>::unpack(ld_stream(a.m + v * 8 + 4 * h), m);
-      Pack<float>::unpack(ld_stream(a.v + v * 8 + 4 * h), vv);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float gr = g[4 * h + k] * a.gscale;
-        m[k] = a.b1 * m[k] + (1.f - a.b1) * gr;
-        vv[k] = a.b2 * vv[k] + (1.f - a.b2) * gr * gr;
-        const float denom = sqrtf(vv[k]) * inv_bc2_sqrt + a.eps;
-        w[k] = w[k] * (1.f - a.lr * a.wd) - step_size * (m[k] / denom);
-        o[4 * h + k] = w[k];
-      }
-      st_stream(a.master + v * 8 + 4 * h, Pack<float>::pack(w));
-      st_stream(a.m + v * 8 + 4 * h, Pack<float>::pack(m));
-      st_stream(a.v + v * 8 + 4 * h, Pack<float>::pack(vv));
+    for (int k = 0; k < 8; ++k) {
+      const float gr = g[k] * a.gscale;
+      m[k] = a.b1 * m[k] + (1.f - a.b1) * gr;
+      vv[k] = a.b2 * vv[k] + (1.f - a.b2) * gr * gr;
+      const float denom = sqrtf(vv[k]) * inv_bc2_sqrt + a.eps;
+      w[k] = w[k] * decay - step_size * __fdividef(m[k], denom);
     }
-    st_stream(a.p + v * 8, P8::pack(o));
+    st_stream(a.master + v * 8, Pack<float>::pack(w));
+    st_stream(a.master + v * 8 + 4, Pack<float>::pack(w + 4));
+    st_stream(a.m + v * 8, Pack<float>::pack(m));
+    st_stream(a.m + v * 8 + 4, Pack<float>::pack(m + 4));
+    st_stream(a.v + v * 8, Pack<float>::pack(vv));
+    st_stream(a.v + v * 8 + 4, Pack<float>::pack(vv + 4));
+    st_stream(a.p + v * 8, P8::pack(w));
   }
   if (blockIdx.x == 0) {
     for (size_t k = nvec * 8 + threadIdx.x; k < a.n; k += blockDim.x) {
@@ -325,7 +332,7 @@ __global__ void __launch_bounds__(512) adamw_kernel(AdamArgs a) {
       const float m = a.b1 * a.m[k] + (1.f - a.b1) * gr;
       const float vv = a.b2 * a.v[k] + (1.f - a.b2) * gr * gr;
       const float denom = sqrtf(vv) * inv_bc2_sqrt + a.eps;
-      const float w = a.master[k] * (1.f - a.lr * a.wd) - step_size * (m / denom);
+      const float w = a.master[k] * decay - step_size * (m / denom);
       a.m[k] = m;
       a.v[k] = vv;
       a.master[k] = w;
@@ -471,7 +478,7 @@ void adamw_launch(void* p, float* master, float* m, float* v, const void* g, siz
                   float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
                   const int* gate, cudaStream_t s) {
   AdamArgs a{(bf16*)p, master, m, v, (const bf16*)g, n, lr, b1, b2, eps, wd, bc1, bc2, gscale, gate};
-  adamw_kernel<<<grid_for(n / 8 + 1, 512, 148 * 4), 512, 0, s>>>(a);
+  adamw_kernel<<<grid_for(n / 8 + 1, 512, 148 * 8), 512, 0, s>>>(a);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 

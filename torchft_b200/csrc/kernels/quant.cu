@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(512, 1) q8_allreduce_kernel(Q8Args a) {
       st_stream(mine + poff + g * kGroup + lane * 16, q);
     }
   }
-  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, true)) return;
+  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/true, /*acquire=*/false)) return;
 
   // ---- phase B: fp32 reduce of my slice from every peer, requantise, push ----
   {
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(512, 1) q8_allreduce_kernel(Q8Args a) {
       }
     }
   }
-  if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, true)) return;
+  if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/true, /*acquire=*/true)) return;
 
   // ---- phase C: dequantise chunk b of every slice into the output tensor ----
   for (int s = 0; s < W; ++s) {

@@ -244,10 +244,16 @@ class Manager:
         if torch.cuda.is_available() and os.environ.get("TORCHFT_B200_TRANSPORT", "p2p") == "p2p":
             from torchft_b200.checkpointing.p2p_transport import P2PTransport
 
-            return P2PTransport(timeout=self._timeout)
+            # receive IN PLACE into the live tensors: a heal allocates nothing (a second copy
+            # of an 8B model + optimizer state does not fit next to the first in 180 GB)
+            return P2PTransport(timeout=self._timeout, state_dict=self._heal_targets)
         from torchft_b200.checkpointing.http_transport import HTTPTransport
 
         return HTTPTransport(timeout=self._timeout, num_chunks=0)
+
+    def _heal_targets(self) -> Dict[str, object]:
+        """Same pytree shape as ``_manager_state_dict`` (destinations for an in-place heal)."""
+        return {"user": {k: fn() for k, fn in self._user_state_dicts.items()}, "torchft": self.state_dict()}
 
     # ------------------------------------------------------------ state dict
     def allow_state_dict_read(self) -> None:

@@ -179,6 +179,11 @@ class ProcessGroupB200(ProcessGroup):
         return t.is_cuda and t.dtype in _NATIVE_DTYPES and t.is_contiguous() and t.data_ptr() % 16 == 0
 
     def _launch(self, fn: Any, result: object) -> Work:
+        # an earlier kernel already timed out / was aborted: fail fast on the host instead of
+        # queueing more collectives against a peer set that needs reconfiguring
+        latched = self._comm.errored() or self._aborted
+        if latched is not None:
+            raise latched
         cur = torch.cuda.current_stream(self._device)
         self._stream.wait_stream(cur)
         with torch.cuda.stream(self._stream):
