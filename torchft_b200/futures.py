@@ -118,7 +118,10 @@ class _TimeoutManager:
             if stuck > limit:
                 sys.stderr.write(f"torchft_b200: timeout thread stuck for {stuck:.1f}s (> {limit}s); exiting\n")
                 sys.stderr.flush()
-                sys.exit(1)
+                try:
+                    sys.exit(1)
+                except SystemExit:
+                    os._exit(1)  # sys.exit from a non-main thread only ends the thread
 
     # -- api ---------------------------------------------------------------
     def call_later(self, timeout: timedelta, cb: Callable[[], None]) -> _Handle:
