@@ -55,11 +55,11 @@ def _advertise_host() -> str:
         return "127.0.0.1"
 T = TypeVar("T")
 
-CHUNK_BYTES = 1 << 20
+CHUNK_BYTES = 4 << 20
 
 
 def device_copy(entries: Sequence[Tuple[int, int, int]], stream: Optional[torch.cuda.Stream] = None,
-                blocks: int = 64, chunk_bytes: int = CHUNK_BYTES) -> None:
+                blocks: int = 128, chunk_bytes: int = CHUNK_BYTES) -> None:
     """Copy ``(src_ptr, dst_ptr, nbytes)`` ranges with one ``heal_copy`` kernel launch.
 
     Either side may be a mapped peer pointer; the kernel issues the NVLink loads.
@@ -97,7 +97,7 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
     """Receiver-pull heal over NVLink. Falls back to host pickling for CPU tensors."""
 
     def __init__(self, timeout: timedelta = timedelta(seconds=60),
-                 state_dict: Optional[Callable[[], T]] = None, blocks: int = 64) -> None:
+                 state_dict: Optional[Callable[[], T]] = None, blocks: int = 128) -> None:
         self._timeout = timeout
         self._inplace_state_dict = state_dict
         self._blocks = blocks

@@ -16,7 +16,7 @@ struct StatusBlock;
 void allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* user_in,
                       void* user_out, size_t nelem, int dtype, int op, float scale,
                       uint64_t flag, int channel, int contribute, int algo, int blocks,
-                      int threads, cudaStream_t stream);
+                      int threads, int barrier_mode, cudaStream_t stream);
 
 // quant.cu -------------------------------------------------------------------
 size_t q8_ngroups(size_t nelem, int world);
@@ -35,7 +35,7 @@ void q8_reduce_raw_launch(const void* const* srcs_dev, int nsrc, int first, size
                           size_t g_hi, float post_scale, void* dst, cudaStream_t stream);
 void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* in_a,
                          const void* in_b, void* out, size_t nelem, int dtype, float post_scale,
-                         uint64_t flag, int channel, int contribute, int blocks,
+                         uint64_t flag, int channel, int contribute, int blocks, int barrier_mode,
                          cudaStream_t stream);
 
 // model_ops.cu ---------------------------------------------------------------

@@ -186,14 +186,14 @@ PYBIND11_MODULE(_K, m) {
       "allreduce",
       [](const PeerTableH& pt, const Status& st, size_t off, uintptr_t user_in, uintptr_t user_out,
          size_t nelem, int dtype, int op, float scale, uint64_t flag, int channel, bool contribute,
-         int algo, int blocks, int threads, uintptr_t stream) {
+         int algo, int blocks, int threads, int barrier_mode, uintptr_t stream) {
         allreduce_launch(pt.pt, st.dev(), off, P<void>(user_in), P<void>(user_out), nelem, dtype, op,
-                         scale, flag, channel, contribute ? 1 : 0, algo, blocks, threads, S(stream));
+                         scale, flag, channel, contribute ? 1 : 0, algo, blocks, threads, barrier_mode, S(stream));
       },
       py::arg("pt"), py::arg("status"), py::arg("off"), py::arg("user_in"), py::arg("user_out"),
       py::arg("nelem"), py::arg("dtype"), py::arg("op"), py::arg("scale"), py::arg("flag"),
       py::arg("channel"), py::arg("contribute"), py::arg("algo"), py::arg("blocks"),
-      py::arg("threads"), py::arg("stream"));
+      py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
 
   m.def("q8_ngroups", &q8_ngroups);
   m.def("q8_buffer_bytes", &q8_buffer_bytes);
@@ -227,13 +227,13 @@ PYBIND11_MODULE(_K, m) {
       "q8_allreduce",
       [](const PeerTableH& pt, const Status& st, size_t off, uintptr_t in_a, uintptr_t in_b,
          uintptr_t out, size_t nelem, int dtype, float post_scale, uint64_t flag, int channel,
-         bool contribute, int blocks, uintptr_t stream) {
+         bool contribute, int blocks, int barrier_mode, uintptr_t stream) {
         q8_allreduce_launch(pt.pt, st.dev(), off, P<void>(in_a), P<void>(in_b), P<void>(out), nelem,
-                            dtype, post_scale, flag, channel, contribute ? 1 : 0, blocks, S(stream));
+                            dtype, post_scale, flag, channel, contribute ? 1 : 0, blocks, barrier_mode, S(stream));
       },
       py::arg("pt"), py::arg("status"), py::arg("off"), py::arg("in_a"), py::arg("in_b"),
       py::arg("out"), py::arg("nelem"), py::arg("dtype"), py::arg("post_scale"), py::arg("flag"),
-      py::arg("channel"), py::arg("contribute"), py::arg("blocks"), py::arg("stream"));
+      py::arg("channel"), py::arg("contribute"), py::arg("blocks"), py::arg("barrier_mode"), py::arg("stream"));
 
   m.def("rmsnorm_fwd", [](uintptr_t x, uintptr_t w, uintptr_t y, uintptr_t rstd, int rows, int H,
                           float eps, uintptr_t s) {

@@ -144,28 +144,79 @@ __device__ __forceinline__ bool wait_flag(const uint64_t* flag, uint64_t expecte
 // Block-granular barrier across ranks on channel `ch`: block b of every rank
 // rendezvous with block b of every peer; threads 0..world-1 each own one peer.
 //
-// System-scope fences (MEMBAR.SYS) are the expensive part: run2/run3 showed
-// their cost growing ~1 us per participating CTA, i.e. they serialise chip-wide.
-// So the barrier issues AT MOST ONE release fence and ONE acquire fence per CTA
-// (by thread 0, made cumulative over the CTA by bar.sync), independent of the
-// world size, and the caller says which side it actually needs:
 //   release: this CTA wrote data (to its own or to peer memory) that peers read
 //            after the barrier. Not needed when the data was produced by an
 //            earlier kernel (kernel boundaries already order it).
 //   acquire: this CTA reads peer-written data after the barrier within this
-//            kernel. All such loads use L1-bypassing accesses, so the fence only
-//            pins the ordering required by the PTX memory model.
+//            kernel (all such loads bypass L1).
+//
+// `mode` selects the memory-ordering recipe (tuned on hardware, bench/comm_tune.py):
+//   0  per-peer thread: [fence.sc.sys if release] st.release.sys ; poll ld.acquire.sys
+//   1  per-peer thread: st.release.sys ; poll ld.relaxed.sys ; fence.acq_rel.sys
+//   2  thread 0: [fence.acq_rel.sys if release] ; per-peer st.relaxed.sys ; poll relaxed ;
+//      thread 0: [fence.acq_rel.sys if acquire]          (<= 2 system fences per CTA)
+//   3  like 2 but the flag is published with red.release.sys (atomic max) so the
+//      store cannot linger in a write-combining path
+__device__ __forceinline__ bool wait_flag_acquire(const uint64_t* flag, uint64_t expected,
+                                                  StatusBlock* st, int peer) {
+  if (ld_acquire_sys(flag) >= expected) return true;
+  if (st->error != kOk) return false;
+  const uint64_t t0 = globaltimer_ns();
+  const uint64_t budget = st->timeout_ns;
+  uint32_t spins = 0;
+  while (true) {
+    if (ld_acquire_sys(flag) >= expected) return true;
+    if ((++spins & 0x3ff) == 0) {
+      if (st->abort) {
+        st->error_rank = peer;
+        st->error_seq = (uint32_t)expected;
+        st->error = kErrAborted;
+        return false;
+      }
+      if (globaltimer_ns() - t0 > budget) {
+        st->error_rank = peer;
+        st->error_seq = (uint32_t)expected;
+        st->error = kErrTimeout;
+        __threadfence_system();
+        return false;
+      }
+    }
+    __nanosleep(32);
+  }
+}
+
+__device__ __forceinline__ void red_max_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("red.release.sys.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ bool block_barrier(const PeerTable& pt, int ch, uint64_t flag,
-                                              StatusBlock* st, bool release, bool acquire = true) {
+                                              StatusBlock* st, bool release, bool acquire, int mode) {
   __syncthreads();
   const int t = threadIdx.x;
+  int ok = 1;
+  if (mode <= 1) {
+    if (t < pt.world && t != pt.rank) {
+      if (mode == 0 && release) __threadfence_system();
+      st_release_sys(&pt.pads[t]->sig[ch][blockIdx.x][pt.rank], flag);
+      if (mode == 0) {
+        ok = wait_flag_acquire(&pt.pads[pt.rank]->sig[ch][blockIdx.x][t], flag, st, t) ? 1 : 0;
+      } else {
+        ok = wait_flag(&pt.pads[pt.rank]->sig[ch][blockIdx.x][t], flag, st, t) ? 1 : 0;
+        fence_acq_rel_sys();
+      }
+    }
+    return __syncthreads_and(ok) != 0;
+  }
   if (release) {
     if (t == 0) fence_acq_rel_sys();
     __syncthreads();
   }
-  int ok = 1;
   if (t < pt.world && t != pt.rank) {
-    st_relaxed_sys(&pt.pads[t]->sig[ch][blockIdx.x][pt.rank], flag);
+    uint64_t* remote = &pt.pads[t]->sig[ch][blockIdx.x][pt.rank];
+    if (mode == 3)
+      red_max_release_sys(remote, flag);
+    else
+      st_relaxed_sys(remote, flag);
     ok = wait_flag(&pt.pads[pt.rank]->sig[ch][blockIdx.x][t], flag, st, t) ? 1 : 0;
   }
   ok = __syncthreads_and(ok);

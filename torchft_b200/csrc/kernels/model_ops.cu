@@ -394,7 +394,19 @@ __global__ void __launch_bounds__(512) heal_copy_kernel(const CopyEntry* __restr
     const size_t len = end - start;
     if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
       const size_t nv = len / 16;
-      for (size_t v = threadIdx.x; v < nv; v += blockDim.x) st_stream(d + v * 16, ld_stream(s + v * 16));
+      // 8 x 16 B loads in flight per thread: a peer (NVLink) read has ~2-3 us latency, so
+      // one outstanding load per thread caps a 64-CTA copy at ~240 GB/s (run4); 8 per
+      // thread puts > 4 MB in flight and reaches link bandwidth.
+      constexpr int U = 8;
+      size_t v = threadIdx.x;
+      for (; v + (size_t)(U - 1) * blockDim.x < nv; v += (size_t)U * blockDim.x) {
+        Vec16 r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = ld_stream(s + (v + (size_t)u * blockDim.x) * 16);
+#pragma unroll
+        for (int u = 0; u < U; ++u) st_stream(d + (v + (size_t)u * blockDim.x) * 16, r[u]);
+      }
+      for (; v < nv; v += blockDim.x) st_stream(d + v * 16, ld_stream(s + v * 16));
       for (size_t k = nv * 16 + threadIdx.x; k < len; k += blockDim.x) d[k] = s[k];
     } else {
       for (size_t k = threadIdx.x; k < len; k += blockDim.x) d[k] = s[k];

@@ -233,6 +233,7 @@ struct Q8Args {
   uint64_t flag;
   int channel;
   int contribute;
+  int barrier_mode;
 };
 
 template <typename T, int W>
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(512, 1) q8_allreduce_kernel(Q8Args a) {
       st_stream(mine + poff + g * kGroup + lane * 16, q);
     }
   }
-  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/true, /*acquire=*/false)) return;
+  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/true, /*acquire=*/false, a.barrier_mode)) return;
 
   // ---- phase B: fp32 reduce of my slice from every peer, requantise, push ----
   {
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(512, 1) q8_allreduce_kernel(Q8Args a) {
       }
     }
   }
-  if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/true, /*acquire=*/true)) return;
+  if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/true, /*acquire=*/true, a.barrier_mode)) return;
 
   // ---- phase C: dequantise chunk b of every slice into the output tensor ----
   for (int s = 0; s < W; ++s) {
@@ -459,7 +460,7 @@ static void q8_ar_w(const Q8Args& a, int blocks, cudaStream_t stream) {
 
 void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* in_a,
                          const void* in_b, void* out, size_t nelem, int dtype, float post_scale,
-                         uint64_t flag, int channel, int contribute, int blocks,
+                         uint64_t flag, int channel, int contribute, int blocks, int barrier_mode,
                          cudaStream_t stream) {
   if (blocks < 1 || blocks > kMaxBlocks) throw std::runtime_error("q8_allreduce: bad grid");
   if (off & 15) throw std::runtime_error("q8_allreduce: offset must be 16 B aligned");
@@ -476,6 +477,7 @@ void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const
   a.flag = flag;
   a.channel = channel;
   a.contribute = contribute;
+  a.barrier_mode = barrier_mode;
   if (pt.world < 2) throw std::runtime_error("q8_allreduce: world must be >= 2");
   switch (dtype) {
     case kF32: q8_ar_w<float>(a, blocks, stream); break;

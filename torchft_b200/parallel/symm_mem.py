@@ -99,6 +99,8 @@ class SymmetricComm:
         self._max_blocks = int(os.environ.get("TORCHFT_B200_AR_BLOCKS", "64"))
         self._threads = int(os.environ.get("TORCHFT_B200_AR_THREADS", "512"))
         self._oneshot_max = int(os.environ.get("TORCHFT_B200_ONESHOT_KB", "256")) << 10
+        self._barrier_mode = int(os.environ.get("TORCHFT_B200_BARRIER_MODE", "0"))
+        self._force_plan: Optional[Tuple[int, int]] = None  # (algo, blocks) override for tuning sweeps
         self.launches = 0  # native kernel launches issued (bench reports this)
         self._hostname = socket.gethostname()
 
@@ -215,6 +217,8 @@ class SymmetricComm:
         mid-size messages are not serialised on a handful of SMs (run1 showed 4 CTAs
         at 1 MB cost 28 us vs 17 us for NCCL).
         """
+        if self._force_plan is not None:
+            return self._force_plan
         w = max(self._world, 2)
         oneshot_max = self._oneshot_max * (4 if w == 2 else (2 if w <= 4 else 1))
         if nbytes <= oneshot_max:
@@ -260,7 +264,7 @@ class SymmetricComm:
                 n = t.numel()
                 algo, blocks = self._plan(n * es)
                 K.allreduce(self._tables[seg.name], self._status, off, 0, 0, n, dt, op, scale, self._next_flag(),
-                            _CH_ALLREDUCE, contribute, algo, blocks, self._threads, sp)
+                            _CH_ALLREDUCE, contribute, algo, blocks, self._threads, self._barrier_mode, sp)
                 self.launches += 1
                 return
             if t.data_ptr() % 16:
@@ -272,7 +276,7 @@ class SymmetricComm:
                 algo, blocks = self._plan(n * es)
                 ptr = flat.data_ptr() + lo * es
                 K.allreduce(self._tables["core"], self._status, 0, ptr, ptr, n, dt, op, scale, self._next_flag(),
-                            _CH_ALLREDUCE, contribute, algo, blocks, self._threads, sp)
+                            _CH_ALLREDUCE, contribute, algo, blocks, self._threads, self._barrier_mode, sp)
                 self.launches += 1
 
     def q8_bytes(self, numel: int) -> int:
@@ -315,7 +319,7 @@ class SymmetricComm:
                 blocks = max(4, min(148, (n // 512) // 32 + 1))  # phases A/C are local HBM passes: use the whole chip
                 K.q8_allreduce(self._tables["core"], self._status, 0, fa.data_ptr() + lo * es,
                                (fb.data_ptr() + lo * es) if fb is not None else 0, fo.data_ptr() + lo * es, n, dt,
-                               scale, self._next_flag(), _CH_Q8, contribute, blocks, sp)
+                               scale, self._next_flag(), _CH_Q8, contribute, blocks, self._barrier_mode, sp)
                 self.launches += 1
 
     # ------------------------------------------------------------------ status
