@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(512, 1) allreduce_twoshot_kernel(ARArgs a) {
     }
     const size_t lo = rank * slice + blockIdx.x * chunk;
     const size_t hi = min(min(lo + chunk, (size_t)(rank + 1) * slice), nvec);
-    constexpr int U = (W >= 8) ? 2 : 4;
+    // vectors in flight per thread: peer loads have ~2.5 us latency, so keep U*W >= 16 outstanding
+    constexpr int U = (W >= 8) ? 2 : (W >= 3 ? 4 : 8);
     for (size_t base = lo; base < hi; base += (size_t)blockDim.x * U) {
       Vec16 in[U][W];
 #pragma unroll

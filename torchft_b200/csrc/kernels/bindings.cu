@@ -71,7 +71,9 @@ class PeerTableH {
     }
     pt.rank = rank;
     pt.world = world;
+    pt.timeout_ns = 60ull * 1000 * 1000 * 1000;
   }
+  void set_timeout_ms(double ms) { pt.timeout_ns = (uint64_t)(ms * 1e6); }
   // Same peers/pads, different data segment (e.g. a registered gradient buffer).
   PeerTableH with_data(const std::vector<uintptr_t>& data) const {
     PeerTableH o(*this);
@@ -168,6 +170,7 @@ PYBIND11_MODULE(_K, m) {
       .def(py::init<const std::vector<uintptr_t>&, const std::vector<uintptr_t>&, int, int>(),
            py::arg("data"), py::arg("pads"), py::arg("rank"), py::arg("world"))
       .def("with_data", &PeerTableH::with_data)
+      .def("set_timeout_ms", &PeerTableH::set_timeout_ms)
       .def_property_readonly("rank", &PeerTableH::rank)
       .def_property_readonly("world", &PeerTableH::world);
 

@@ -139,6 +139,8 @@ class SymmetricComm:
         self._timeout = timeout
         if self._status is not None:
             self._status.set_timeout_ms(timeout.total_seconds() * 1e3)
+        for t in self._tables.values():
+            t.set_timeout_ms(timeout.total_seconds() * 1e3)
 
     # --------------------------------------------------------------- configure
     def configure(self, store: Any, rank: int, world: int, epoch: int) -> None:
@@ -197,6 +199,7 @@ class SymmetricComm:
                 pads = core_ptrs  # signal pad sits at offset 0 of the core segment
                 self._tables = {}
                 base = K.PeerTable([p + self._pad_bytes for p in core_ptrs], pads, rank, world)
+                base.set_timeout_ms(self._timeout.total_seconds() * 1e3)
                 self._tables["core"] = base
                 for n in names:
                     if n != "core":
