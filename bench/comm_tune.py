@@ -41,7 +41,7 @@ def timed(fn, iters, warm=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/comm_tune.json")
-    ap.add_argument("--modes", default="0,1,2,3")
+    ap.add_argument("--modes", default="2")
     ap.add_argument("--max-mb", type=int, default=256)
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
@@ -51,7 +51,7 @@ def main():
     comm = SymmetricComm(timeout=timedelta(seconds=20))
     symm = comm.alloc("tune", args.max_mb << 20)
     comm.configure(dist.PrefixStore("tune", store), rank, world, 1)
-    sizes = [1 << k for k in range(12, 31) if (1 << k) <= (args.max_mb << 20)]
+    sizes = [1 << k for k in range(12, 31, 1) if (1 << k) <= (args.max_mb << 20)]
     modes = [int(m) for m in args.modes.split(",")]
     rows = []
     for nbytes in sizes:
@@ -63,7 +63,7 @@ def main():
         best = None
         table = {}
         for algo in (0, 1):
-            for blocks in (1, 2, 4, 8, 16, 32, 64, 128):
+            for blocks in (4, 16, 32, 64, 128):
                 if algo == 0:
                     # in-place one-shot keeps <= 64 KB per block in registers
                     if (nbytes + blocks - 1) // blocks > (64 << 10):

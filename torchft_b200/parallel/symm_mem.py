@@ -99,7 +99,7 @@ class SymmetricComm:
         self._max_blocks = int(os.environ.get("TORCHFT_B200_AR_BLOCKS", "64"))
         self._threads = int(os.environ.get("TORCHFT_B200_AR_THREADS", "512"))
         self._oneshot_max = int(os.environ.get("TORCHFT_B200_ONESHOT_KB", "256")) << 10
-        self._barrier_mode = int(os.environ.get("TORCHFT_B200_BARRIER_MODE", "0"))
+        self._barrier_mode = int(os.environ.get("TORCHFT_B200_BARRIER_MODE", "2"))
         self._force_plan: Optional[Tuple[int, int]] = None  # (algo, blocks) override for tuning sweeps
         self.launches = 0  # native kernel launches issued (bench reports this)
         self._hostname = socket.gethostname()
@@ -213,19 +213,19 @@ class SymmetricComm:
     def _plan(self, nbytes: int) -> Tuple[int, int]:
         """(algo, blocks): identical on every rank for a given message size.
 
-        One-shot (each rank reads everything, 2 barriers, no write-back hop) wins while
-        latency dominates; its per-block chunk is capped at 64 KB (results stay in
-        registers across the closing barrier). Two-shot moves 2(N-1)/N of the bytes and
-        uses both link directions; it gets one CTA per 64 KB up to ``max_blocks`` so
-        mid-size messages are not serialised on a handful of SMs (run1 showed 4 CTAs
-        at 1 MB cost 28 us vs 17 us for NCCL).
+        Table from ``bench/comm_tune.py`` on B200 (profiles/comm_tune_*.json). One-shot (each
+        rank reads the whole message from every peer; two flag exchanges, no write-back hop)
+        wins while (world-1) x bytes still fits the latency budget; it likes MANY small CTAs
+        (16 KB each, <= 64 KB because results stay in registers across the closing barrier).
+        Two-shot moves 2(N-1)/N of the bytes using both link directions; one CTA per 64 KB up
+        to ``max_blocks`` (a comm kernel that overlaps backward should not take every SM).
         """
         if self._force_plan is not None:
             return self._force_plan
         w = max(self._world, 2)
-        oneshot_max = self._oneshot_max * (4 if w == 2 else (2 if w <= 4 else 1))
+        oneshot_max = self._oneshot_max * (8 if w == 2 else (4 if w <= 4 else 2))
         if nbytes <= oneshot_max:
-            blocks = max(1, min(32, (nbytes + (32 << 10) - 1) // (32 << 10)))
+            blocks = max(1, min(128, (nbytes + (16 << 10) - 1) // (16 << 10)))
             if (nbytes + blocks - 1) // blocks <= (64 << 10):
                 return 0, blocks
         blocks = max(8, min(self._max_blocks, nbytes // (64 << 10)))
