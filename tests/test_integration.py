@@ -32,6 +32,9 @@ from torchft_b200.process_group import FakeProcessGroupWrapper, ProcessGroupGloo
 logger = logging.getLogger(__name__)
 
 
+_INIT_LOCK = threading.Lock()
+
+
 class InjectedFailure(Exception):
     pass
 
@@ -108,6 +111,7 @@ class Runner:
     use_async_quorum: bool = True
     init_sync: bool = True
     transport: str = "http"
+    same_init: bool = False
     manager_kwargs: Dict[str, Any] = field(default_factory=dict)
 
     def run(self) -> List[Dict[str, Any]]:
@@ -134,8 +138,10 @@ class Runner:
             return out
 
     def _train(self, rank: int, store_port: int) -> Dict[str, Any]:
-        torch.manual_seed(1000 * self.replica_id + rank)  # different init per replica: init_sync must fix it
-        m = MyModel()
+        with _INIT_LOCK:  # the global RNG is shared by all replica threads
+            # different init per replica unless same_init: init_sync must make them equal
+            torch.manual_seed(0 if self.same_init else 1000 * self.replica_id + rank)
+            m = MyModel()
         opt_inner = optim.Adam(m.parameters(), lr=0.05)
         pg = FakeProcessGroupWrapper(ProcessGroupGloo(timeout=timedelta(seconds=10)))
 
@@ -217,23 +223,7 @@ def test_ddp_recovery_after_replica_crash(lighthouse, use_async_quorum):
 def test_ddp_skip_init_sync(lighthouse):
     """init_sync=False: replicas that start identical stay identical without a step-0 transfer."""
     inj = EventInjector()
-
-    class SameInit(Runner):
-        def _train(self, rank, store_port):
-            return super()._train(rank, store_port)
-
-    runners = [Runner(i, lighthouse.address(), inj, init_sync=False) for i in range(2)]
-    # identical seeds => identical init
-    for r in runners:
-        r.replica_id = r.replica_id
-    # patch seed: both replicas use seed 0
-    orig = torch.manual_seed
-    res = None
-    try:
-        torch.manual_seed = lambda s: orig(0)  # type: ignore[assignment]
-        res = _run(runners)
-    finally:
-        torch.manual_seed = orig  # type: ignore[assignment]
+    res = _run([Runner(i, lighthouse.address(), inj, init_sync=False, same_init=True) for i in range(2)])
     _assert_equal_state(res)
 
 

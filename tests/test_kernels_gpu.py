@@ -181,3 +181,33 @@ def test_llama_tiny_fwd_bwd_matches_reference():
         assert p.grad is not None, name
         r = _rel(p.grad, ref_grads[name])
         assert r < 0.1, (name, r)
+
+
+def test_direct_wgrad_into_flat_buffer_matches_accumulate_path():
+    """reset_grads(): wgrad GEMMs write the flat gradient buffer directly; result == zero+accumulate path."""
+    from torchft_b200.models.llama import CONFIGS, FlatParams, Llama
+
+    cfg = CONFIGS["llama3_tiny"]
+    tok = torch.randint(0, cfg.vocab_size, (2, 64), device="cuda")
+    tgt = torch.randint(0, cfg.vocab_size, (2, 64), device="cuda")
+    grads = []
+    for direct in (False, True):
+        m = Llama(cfg, device="meta")
+        flat = FlatParams(m, device=torch.device("cuda"))
+        m.init_weights(0)
+        flat.grad.fill_(float("nan")) if direct else None  # stale garbage must be fully overwritten
+        flat.grad.view(torch.int16).zero_() if not direct else None
+        if direct:
+            # padding between parameters is never written by producers: it must start (and stay) zero
+            flat.grad.zero_()
+            for p in flat.params:
+                p._flat_grad.fill_(float("nan"))
+        flat.reset_grads(zero=not direct)
+        m(tok, tgt).backward()
+        for p in flat.params:
+            flat.adopt_grad(p)
+        torch.cuda.synchronize()
+        assert not torch.isnan(flat.grad.float()).any()
+        grads.append(flat.grad.float().clone())
+    rel = (grads[0] - grads[1]).norm() / grads[0].norm()
+    assert rel < 1e-2, rel

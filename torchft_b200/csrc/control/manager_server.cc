@@ -99,16 +99,25 @@ Quorum ManagerServer::quorum_with_retries(const QuorumMember& requester, Millis 
   int64_t retry = 0;
   while (true) {
     int64_t sleep_ms = 100;
+    bool timed_out = false;
+    std::string last;
     try {
       return lighthouse_client(false)->quorum(requester, timeout);
     } catch (const TimeoutError& e) {
+      timed_out = true;
+      last = e.what();
       log_replica(replica_id_, std::string("lighthouse quorum timeout. error: ") + e.what());
     } catch (const std::exception& e) {
+      last = e.what();
       log_replica(replica_id_, std::string("lighthouse quorum failed. error: ") + e.what());
       sleep_ms = std::max<int64_t>(100, timeout.count() / std::max<int64_t>(quorum_retries_ + 1, 1));
     }
-    if (retry == quorum_retries_)
-      throw RpcError(kStatusInternal, "lighthouse quorum failed after " + std::to_string(retry) + " retries.");
+    if (retry == quorum_retries_) {
+      // A deadline stays a deadline for the group's waiters (Python TimeoutError), whichever of
+      // "their own wait expired" / "the forwarded request expired" is observed first.
+      if (timed_out) throw TimeoutError("lighthouse quorum timed out after " + std::to_string(retry) + " retries: " + last);
+      throw RpcError(kStatusInternal, "lighthouse quorum failed after " + std::to_string(retry) + " retries: " + last);
+    }
     {
       std::unique_lock<std::mutex> lk(mu_);
       if (cv_.wait_for(lk, Millis(sleep_ms), [this] { return shutdown_; }))

@@ -110,6 +110,7 @@ class FlatDistributedDataParallel(nn.Module):
         self._works = []
 
     def _on_grad(self, p: torch.Tensor) -> None:
+        self._flat.adopt_grad(p)  # no-op when the producer already wrote into the flat buffer
         bi = self._param_bucket[id(p)]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
@@ -124,7 +125,10 @@ class FlatDistributedDataParallel(nn.Module):
         # parameters that received no gradient this step still need their bucket reduced
         for bi, left in enumerate(self._pending):
             if left > 0:
-                start, end, _ = self._buckets[bi]
+                start, end, params = self._buckets[bi]
+                for q in params:
+                    if q.grad is None:
+                        self._flat.adopt_grad(q)  # unused parameter this step: contributes zeros
                 self._works.append(self._manager.allreduce(self._flat.grad[start:end], should_quantize=self._quantize))
         for w in self._works:
             w.wait()

@@ -94,7 +94,7 @@ class Block(nn.Module):
             enable_gqa=cfg.n_kv_heads != cfg.n_heads,
         )
         o = o.transpose(1, 2).reshape(B, S, d)
-        h = x + o @ self.wo.t()
+        h = x + fused.linear(o, self.wo)
         gu = fused.norm_linear(h, self.ffn_norm, self.w13, cfg.norm_eps)
         return h + fused.swiglu_linear(gu, self.w2)
 
@@ -200,8 +200,31 @@ class FlatParams:
                 else:
                     v.copy_(p.data)
                     p.data = v
-                p.grad = self.grad[o : o + p.numel()].view(p.shape)
+                p._flat_grad = self.grad[o : o + p.numel()].view(p.shape)  # wgrad GEMMs write here directly
+                p.grad = p._flat_grad
                 self.params.append(p)
+
+    def reset_grads(self, zero: bool = False) -> None:
+        """Start a step: with ``zero=False`` every ``p.grad`` is dropped so producers write their
+        gradient straight into the flat buffer (no memset, no accumulate pass); ``zero=True`` keeps
+        the classic zeroed-views behaviour (needed for gradient accumulation over micro-batches)."""
+        if zero:
+            self.grad.zero_()
+            for p in self.params:
+                p.grad = p._flat_grad
+        else:
+            for p in self.params:
+                p.grad = None
+
+    def adopt_grad(self, p: nn.Parameter) -> None:
+        """Make sure ``p.grad`` IS its slice of the flat buffer (copy if autograd produced it elsewhere)."""
+        g = p.grad
+        slot = p._flat_grad
+        if g is None:
+            slot.zero_()
+        elif g.data_ptr() != slot.data_ptr():
+            slot.copy_(g)
+        p.grad = slot
 
     def buckets(self, bucket_elems: int) -> List[Tuple[int, int, List[nn.Parameter]]]:
         """Contiguous (start, end, params) buckets in gradient-production order."""

@@ -15,6 +15,18 @@ import torch
 from torchft_b200.ops import _native
 
 
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """dW = dy2^T @ x2. When ``W`` lives in a FlatParams buffer and has no gradient yet, the GEMM
+    writes STRAIGHT into W's slice of the flat (NVLink-symmetric) gradient buffer and returns that
+    view; autograd then adopts it as ``W.grad`` without a copy. This removes the per-step
+    zero-fill of the gradient buffer and the read-modify-write accumulation pass (~64 GB of HBM
+    traffic per step for an 8B model): the wgrad epilogue IS the bucket write."""
+    slot = getattr(W, "_flat_grad", None)
+    if slot is not None and W.grad is None and slot.dtype == dy2.dtype:
+        return torch.mm(dy2.t(), x2, out=slot.view(W.shape))
+    return dy2.t() @ x2
+
+
 def _chk(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda or t.dtype != torch.bfloat16:
         raise TypeError(f"{name} must be a bf16 CUDA tensor, got {t.dtype} on {t.device}")
@@ -161,7 +173,10 @@ class _LinearCrossEntropy(torch.autograd.Function):
         n_valid = max(int((target != ignore_index).sum().item()), 1) if count_valid else T
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         dh = torch.empty_like(h) if need_grad else None
-        dW = torch.zeros_like(weight) if need_grad else None
+        slot = getattr(weight, "_flat_grad", None)
+        direct = need_grad and slot is not None and weight.grad is None
+        dW = (slot.view(weight.shape).zero_() if direct else torch.zeros_like(weight)) if need_grad else None
+        ctx.direct = direct
         losses = torch.empty(T, dtype=torch.float32, device=h.device)
         sp = _native.stream_ptr()
         for lo in range(0, T, chunk):
@@ -185,7 +200,8 @@ class _LinearCrossEntropy(torch.autograd.Function):
         dh, dW = ctx.saved_tensors
         # g is the upstream scalar (1.0 for a plain loss.backward()); fold it in
         # without a host sync.
-        return dh * g.to(dh.dtype), dW * g.to(dW.dtype), None, None, None, None
+        # (dW already sits in the flat gradient buffer when ctx.direct; scale in place)
+        return dh * g.to(dh.dtype), (dW.mul_(g.to(dW.dtype)) if ctx.direct else dW * g.to(dW.dtype)), None, None, None, None
 
 
 def linear_cross_entropy(h: torch.Tensor, weight: torch.Tensor, target: torch.Tensor, chunk: int = 2048,
@@ -225,10 +241,14 @@ class FlatAdamW:
         self.v = torch.zeros_like(self.master)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.t = 0
+        self.direct_grads = False
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay, "params": [flat_param]}]
 
     def zero_grad(self, set_to_none: bool = False) -> None:
-        self.g.zero_()
+        # direct_grads: producers overwrite the whole flat buffer every step
+        # (FlatParams.reset_grads + ops.fused._wgrad), so the 2-bytes/param memset is skipped.
+        if not self.direct_grads:
+            self.g.zero_()
 
     def step(self, grad_scale: float = 1.0, gate: Optional[torch.Tensor] = None) -> None:
         K = _native.load()
@@ -287,7 +307,7 @@ class _NormLinear(torch.autograd.Function):
         dy2 = dy.reshape(rows, -1)
         n = torch.empty_like(x)
         K.rmsnorm_fwd(x.data_ptr(), g.data_ptr(), n.data_ptr(), rstd.data_ptr(), rows, H, ctx.eps, sp)
-        dW = dy2.t() @ n.view(rows, H)
+        dW = _wgrad(dy2, n.view(rows, H), W)
         dn = dy2 @ W
         dx = n  # reuse the recompute buffer for dx
         grid = K.rmsnorm_bwd_grid(rows)
@@ -330,7 +350,7 @@ class _SwiGLULinear(torch.autograd.Function):
         d2 = dout.reshape(T, -1)
         a = torch.empty((T, F), dtype=gu.dtype, device=gu.device)
         K.swiglu_fwd(gu.data_ptr(), a.data_ptr(), T, F, sp)
-        dW2 = d2.t() @ a
+        dW2 = _wgrad(d2, a, W2)
         da = torch.mm(d2, W2, out=a)  # reuse buffer
         dgu = torch.empty_like(gu)
         K.swiglu_bwd(da.data_ptr(), gu.data_ptr(), dgu.data_ptr(), T, F, sp)
@@ -340,3 +360,24 @@ class _SwiGLULinear(torch.autograd.Function):
 def swiglu_linear(gate_up: torch.Tensor, W2: torch.Tensor) -> torch.Tensor:
     """``(silu(gate) * up) @ W2.T`` with the activation product recomputed in backward."""
     return _SwiGLULinear.apply(gate_up, W2)
+
+
+class _Linear(torch.autograd.Function):
+    """y = x @ W^T whose weight gradient is written straight into the flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, W: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
+        ctx.save_for_backward(x, W)
+        return x @ W.t()
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):  # type: ignore[override]
+        x, W = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dW = _wgrad(dy2, x.reshape(-1, x.shape[-1]), W)
+        return (dy2 @ W).view(x.shape), dW
+
+
+def linear(x: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """``x @ W.T`` with the wgrad GEMM writing directly into the flat gradient bucket."""
+    return _Linear.apply(x, W)

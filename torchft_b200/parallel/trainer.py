@@ -84,6 +84,7 @@ class FaultTolerantTrainer:
         self.flat = FlatParams(self.model, grad_alloc=grad_alloc, device=self.device)
         self.model.init_weights(seed)
         self.inner_optim = FlatAdamW(self.flat.param, self.flat.grad, lr=lr)
+        self.inner_optim.direct_grads = True  # step_device() drops p.grad; wgrad GEMMs fill the flat buffer
 
         self.manager = Manager(
             pg=self.pg,
@@ -124,7 +125,8 @@ class FaultTolerantTrainer:
     # -------------------------------------------------------------------- step
     def step_device(self, tokens: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         """One fault-tolerant optimisation step on device-resident inputs; returns the loss tensor (device)."""
-        self.optim.zero_grad()            # start_quorum (async) + zero the flat gradient
+        self.optim.zero_grad(set_to_none=True)  # start_quorum (async); no memset:
+        self.flat.reset_grads()                  # wgrad GEMMs write the flat gradient buffer directly
         loss = self.ddp(tokens, targets)  # forward (fused kernels + cuBLAS + SDPA)
         loss.backward()                   # bucket all-reduces launch from grad hooks, overlapped
         self.ddp.finish()                 # current stream waits for the comm stream
