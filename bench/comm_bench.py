@@ -90,6 +90,10 @@ def main() -> None:
     dist.all_reduce(rt, op=dist.ReduceOp.MAX)
     res["reconfigure"] = dict(zip(["native_first_ms", "native_remap_avg_ms", "native_remap_min_ms", "nccl_new_comm_avg_ms", "nccl_new_comm_min_ms"], [round(v, 3) for v in rt.tolist()]))
 
+    res["symm_mode"] = comm._mode
+    res["nvls"] = bool(comm._mc)
+    if comm._mc:
+        comm._nvls_min = 4096  # make the correctness sweep below cover the NVLS kernel as well
     # ---- correctness vs fp32 reference (bit-level vs NCCL is order dependent) ----
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     for dtype in (torch.float32, torch.bfloat16, torch.float16):
@@ -113,6 +117,15 @@ def main() -> None:
                 ok = err <= tol * max(1.0, ref.abs().max().item())
                 e = comm.errored()
                 res["correctness"].append({"dtype": str(dtype), "n": n, "path": path, "max_err": err, "ok": bool(ok) and e is None, "err": str(e) if e else None})
+    if comm._mc:
+        # NVLS with a non-participant (zeroes its own copy first) on the symmetric segment
+        n = 1 << 18
+        buf = symm[: n * 4].view(torch.float32)
+        buf.fill_(float(rank + 1))
+        comm.allreduce_(buf, scale=0.5, contribute=(rank != 0))
+        torch.cuda.synchronize()
+        expect = 0.5 * sum(r + 1 for r in range(1, world))
+        res["correctness"].append({"case": "nvls_non_participant", "ok": bool((buf == expect).all().item())})
     # non-participant contributes zeros
     x = torch.full((4096,), float(rank + 1), device="cuda")
     comm.allreduce_(x, scale=1.0, contribute=(rank != 0))
@@ -154,12 +167,22 @@ def main() -> None:
         buf.normal_()
         x = torch.randn(n, device="cuda").to(torch.bfloat16)
         busf = 2 * (world - 1) / world
+        nvls_min_saved = comm._nvls_min
+        comm._nvls_min = 1 << 62  # P2P kernels only in this column
         for nb in block_opts:
             comm._max_blocks = nb
             ms = device_time_ms(lambda: comm.allreduce_(buf, scale=1.0 / world), iters, 3)
             row[f"native_symm_b{nb}_ms"] = round(ms, 5)
             row[f"native_symm_b{nb}_busbw_gbs"] = round(nbytes * busf / ms / 1e6, 1)
+        comm._nvls_min = nvls_min_saved
         comm._max_blocks = block_opts[-1]
+        if comm._mc:  # VMM mode with an NVLS multicast object: time the in-switch reduction too
+            saved = comm._nvls_min
+            comm._nvls_min = 0
+            ms = device_time_ms(lambda: comm.allreduce_(buf, scale=1.0 / world), iters, 3)
+            row["native_nvls_ms"] = round(ms, 5)
+            row["native_nvls_busbw_gbs"] = round(nbytes * busf / ms / 1e6, 1)
+            comm._nvls_min = saved
         ms = device_time_ms(lambda: comm.allreduce_(x, scale=1.0 / world), iters, 3)
         row["native_staged_ms"] = round(ms, 5)
         row["native_staged_busbw_gbs"] = round(nbytes * busf / ms / 1e6, 1)

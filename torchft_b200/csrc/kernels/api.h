@@ -18,6 +18,11 @@ void allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const vo
                       uint64_t flag, int channel, int contribute, int algo, int blocks,
                       int threads, int barrier_mode, cudaStream_t stream);
 
+// allreduce_nvls.cu ---------------------------------------------------------
+void allreduce_nvls_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, size_t off, size_t nelem, int dtype,
+                           float scale, uint64_t flag, int channel, int contribute, int blocks, int threads,
+                           int barrier_mode, cudaStream_t stream);
+
 // quant.cu -------------------------------------------------------------------
 size_t q8_ngroups(size_t nelem, int world);
 size_t q8_buffer_bytes(size_t nelem, int world);

@@ -148,6 +148,8 @@ bool can_access_peer(int dev, int peer) {
 
 }  // namespace
 
+void bind_vmm(py::module_& m);  // vmm.cu
+
 PYBIND11_MODULE(_K, m) {
   m.doc() = "torchft_b200 data-plane kernels (sm_100a): P2P all-reduce, q8 all-reduce, heal copy, model ops";
   m.attr("MAX_RANKS") = kMaxRanks;
@@ -196,6 +198,18 @@ PYBIND11_MODULE(_K, m) {
       py::arg("pt"), py::arg("status"), py::arg("off"), py::arg("user_in"), py::arg("user_out"),
       py::arg("nelem"), py::arg("dtype"), py::arg("op"), py::arg("scale"), py::arg("flag"),
       py::arg("channel"), py::arg("contribute"), py::arg("algo"), py::arg("blocks"),
+      py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
+
+  bind_vmm(m);
+  m.def(
+      "allreduce_nvls",
+      [](const PeerTableH& pt, const Status& st, uintptr_t mc_base, size_t off, size_t nelem, int dtype, float scale,
+         uint64_t flag, int channel, bool contribute, int blocks, int threads, int barrier_mode, uintptr_t stream) {
+        allreduce_nvls_launch(pt.pt, st.dev(), P<void>(mc_base), off, nelem, dtype, scale, flag, channel,
+                              contribute ? 1 : 0, blocks, threads, barrier_mode, S(stream));
+      },
+      py::arg("pt"), py::arg("status"), py::arg("mc_base"), py::arg("off"), py::arg("nelem"), py::arg("dtype"),
+      py::arg("scale"), py::arg("flag"), py::arg("channel"), py::arg("contribute"), py::arg("blocks"),
       py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
 
   m.def("q8_ngroups", &q8_ngroups);

@@ -23,6 +23,7 @@ import json
 import os
 import socket
 import threading
+import time
 from dataclasses import dataclass, field
 from datetime import timedelta
 from typing import Any, Dict, List, Optional, Tuple
@@ -58,13 +59,16 @@ def tensor_from_ptr(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor
 
 @dataclass
 class Segment:
-    """A cudaMalloc'ed region exported to peers over CUDA IPC."""
+    """A device region exported to peers: cudaMalloc + CUDA IPC ("ipc" mode) or a refcounted VMM
+    allocation shared as a POSIX fd ("vmm" mode; required for NVLS multicast)."""
 
     name: str
     ptr: int
     nbytes: int
     handle: bytes
     tensor: torch.Tensor  # uint8 view keeping python-side references simple
+    mem_handle: int = 0   # CUmemGenericAllocationHandle (vmm mode)
+    fd: int = -1          # exported descriptor (vmm mode)
 
     def contains(self, p: int, n: int) -> bool:
         return self.ptr <= p and p + n <= self.ptr + self.nbytes
@@ -99,6 +103,13 @@ class SymmetricComm:
         self._max_blocks = int(os.environ.get("TORCHFT_B200_AR_BLOCKS", "64"))
         self._threads = int(os.environ.get("TORCHFT_B200_AR_THREADS", "512"))
         self._oneshot_max = int(os.environ.get("TORCHFT_B200_ONESHOT_KB", "256")) << 10
+        # "vmm": cuMemCreate-backed segments (survive exporter death, NVLS-capable); "ipc": cudaMalloc + cudaIpc
+        self._mode = os.environ.get("TORCHFT_B200_SYMM", "ipc")
+        self._nvls_enabled = os.environ.get("TORCHFT_B200_NVLS", "1") != "0"
+        self._nvls_min = int(os.environ.get("TORCHFT_B200_NVLS_MIN_KB", "512")) << 10
+        self._fdserver: Any = None
+        self._peer_vmm: Dict[Tuple[str, int, str], Tuple[int, int, int]] = {}  # (host, pid, seg) -> (va, handle, size)
+        self._mc: Dict[str, Tuple[int, int, int]] = {}  # segment -> (mc handle, multicast va, size)
         self._barrier_mode = int(os.environ.get("TORCHFT_B200_BARRIER_MODE", "2"))
         self._force_plan: Optional[Tuple[int, int]] = None  # (algo, blocks) override for tuning sweeps
         self.launches = 0  # native kernel launches issued (bench reports this)
@@ -114,10 +125,22 @@ class SymmetricComm:
 
     def _alloc_segment(self, name: str, nbytes: int) -> Segment:
         nbytes = (nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        K = self._K
         with torch.cuda.device(self.device):
-            ptr = self._K.symm_alloc(nbytes)
-            handle = self._K.ipc_get_handle(ptr)
-        seg = Segment(name, ptr, nbytes, handle, tensor_from_ptr(ptr, nbytes, self.device))
+            if self._mode == "vmm":
+                if self._fdserver is None:
+                    self._fdserver = K.FdServer()
+                gran = K.vmm_granularity()
+                if self._nvls_enabled and K.multicast_supported():
+                    gran = max(gran, K.mc_granularity(2, max(nbytes, gran)))
+                nbytes = (nbytes + gran - 1) // gran * gran
+                ptr, size, mem_handle, fd = K.vmm_alloc(nbytes)
+                self._fdserver.publish(name, fd)
+                seg = Segment(name, ptr, size, b"", tensor_from_ptr(ptr, size, self.device), mem_handle, fd)
+            else:
+                ptr = K.symm_alloc(nbytes)
+                handle = K.ipc_get_handle(ptr)
+                seg = Segment(name, ptr, nbytes, handle, tensor_from_ptr(ptr, nbytes, self.device))
         self._segments[name] = seg
         return seg
 
@@ -158,6 +181,8 @@ class SymmetricComm:
                     "pid": os.getpid(),
                     "device": self.device.index,
                     "floor": self._flag,
+                    "mode": self._mode,
+                    "fd_server": self._fdserver.name() if self._fdserver is not None else "",
                     "segments": {n: {"handle": s.handle.hex(), "nbytes": s.nbytes} for n, s in self._segments.items()},
                 }
                 store.set(f"symm/{rank}", json.dumps(desc))
@@ -171,12 +196,28 @@ class SymmetricComm:
                     for n in names:
                         if d["segments"][n]["nbytes"] != self._segments[n].nbytes:
                             raise RuntimeError(f"segment {n!r} size mismatch on rank {r}")
+                self._release_multicast()
                 needed: Dict[Tuple[str, int, bytes], int] = {}
+                needed_vmm: Dict[Tuple[str, int, str], Tuple[int, int, int]] = {}
                 ptrs: Dict[str, List[int]] = {n: [] for n in names}
                 for r, d in enumerate(descs):
+                    if d.get("mode", "ipc") != self._mode:
+                        raise RuntimeError(f"rank {r} uses symmetric-memory mode {d.get('mode')!r}, we use {self._mode!r}")
                     for n in names:
                         if r == rank:
                             ptrs[n].append(self._segments[n].ptr)
+                            continue
+                        if d["host"] != self._hostname:
+                            raise RuntimeError("peer-memory transport requires all replicas on one NVSwitch domain (same host)")
+                        if self._mode == "vmm":
+                            vkey = (d["host"], int(d["pid"]), n)
+                            ent = self._peer_vmm.get(vkey)
+                            if ent is None:
+                                fd = K.fetch_fd(d["fd_server"], n)
+                                va, h = K.vmm_import(fd, self._segments[n].nbytes)
+                                ent = (va, h, self._segments[n].nbytes)
+                            needed_vmm[vkey] = ent
+                            ptrs[n].append(ent[0])
                             continue
                         h = bytes.fromhex(d["segments"][n]["handle"])
                         key = (d["host"], int(d["pid"]), h)
@@ -195,6 +236,10 @@ class SymmetricComm:
                         except RuntimeError:
                             pass  # exporter already gone
                 self._peer_ptrs = needed
+                for vkey, (va, h, size) in list(self._peer_vmm.items()):
+                    if vkey not in needed_vmm:
+                        K.vmm_unmap(va, size, h)  # our reference kept the memory alive even if the peer died
+                self._peer_vmm = needed_vmm
                 core_ptrs = ptrs["core"]
                 pads = core_ptrs  # signal pad sits at offset 0 of the core segment
                 self._tables = {}
@@ -207,7 +252,49 @@ class SymmetricComm:
                 floor = max(int(d["floor"]) for d in descs)
                 self._flag = max(floor, int(epoch) << 32) + 16
                 self._rank, self._world, self._epoch = rank, world, int(epoch)
+                if self._mode == "vmm" and self._nvls_enabled and world > 1 and K.multicast_supported():
+                    self._setup_multicast(store, descs, [n for n in names if n != "core"], rank, world)
                 self._configured = True
+
+    # --------------------------------------------------------------- multicast
+    def _store_barrier(self, store: Any, key: str, world: int) -> None:
+        n = store.add(key, 1)
+        deadline = time.monotonic() + self._timeout.total_seconds()
+        while n < world:
+            if time.monotonic() > deadline:
+                raise TimeoutError(f"store barrier {key} timed out ({n}/{world})")
+            time.sleep(0.0005)
+            n = store.add(key, 0)
+
+    def _setup_multicast(self, store: Any, descs: List[Dict[str, Any]], names: List[str], rank: int, world: int) -> None:
+        """One NVLS multicast object per user segment over the CURRENT quorum (objects are bound to a
+        fixed device set, so they are re-created -- cheaply -- on every membership change)."""
+        K = self._K
+        for n in names:
+            seg = self._segments[n]
+            key = f"mc:{n}:{self._epoch}:{self._flag}"
+            if rank == 0:
+                mc, fd = K.mc_create(world, seg.nbytes)
+                self._fdserver.publish(key, fd)
+                store.set(f"mcready/{n}", key)
+            else:
+                key = bytes(store.get(f"mcready/{n}")).decode()
+                mc = K.mc_import(K.fetch_fd(descs[0]["fd_server"], key))
+            K.mc_add_device(mc)
+            self._store_barrier(store, f"mcadd/{n}", world)
+            va = K.mc_bind_and_map(mc, seg.mem_handle, seg.nbytes)
+            self._store_barrier(store, f"mcbind/{n}", world)
+            if rank == 0:
+                self._fdserver.unpublish(key)
+            self._mc[n] = (mc, va, seg.nbytes)
+
+    def _release_multicast(self) -> None:
+        for n, (mc, va, size) in list(self._mc.items()):
+            try:
+                self._K.mc_release(mc, va, size)
+            except Exception:  # noqa: BLE001
+                pass
+        self._mc = {}
 
     # ------------------------------------------------------------- collectives
     def _plan(self, nbytes: int) -> Tuple[int, int]:
@@ -265,6 +352,14 @@ class SymmetricComm:
             if hit is not None and hit[0].name != "core" and hit[1] % 16 == 0:
                 seg, off = hit
                 n = t.numel()
+                mc = self._mc.get(seg.name)
+                if (mc is not None and op == _native.OP_SUM and n * es >= self._nvls_min and self._world > 1
+                        and self._force_plan is None):
+                    blocks = max(8, min(self._max_blocks, (n * es) // (64 << 10)))
+                    K.allreduce_nvls(self._tables[seg.name], self._status, mc[1], off, n, dt, scale, self._next_flag(),
+                                     _CH_ALLREDUCE, contribute, blocks, self._threads, self._barrier_mode, sp)
+                    self.launches += 1
+                    return
                 algo, blocks = self._plan(n * es)
                 K.allreduce(self._tables[seg.name], self._status, off, 0, 0, n, dt, op, scale, self._next_flag(),
                             _CH_ALLREDUCE, contribute, algo, blocks, self._threads, self._barrier_mode, sp)
@@ -361,12 +456,19 @@ class SymmetricComm:
                 torch.cuda.synchronize(self.device)
             except RuntimeError:
                 pass
+            self._release_multicast()
             for p in self._peer_ptrs.values():
                 try:
                     K.ipc_close_handle(p)
                 except RuntimeError:
                     pass
             self._peer_ptrs = {}
+            for va, h, size in self._peer_vmm.values():
+                try:
+                    K.vmm_unmap(va, size, h)
+                except Exception:  # noqa: BLE001
+                    pass
+            self._peer_vmm = {}
             self._tables = {}
             self._configured = False
             # local segments are intentionally leaked until process exit if a
