@@ -1,0 +1,217 @@
+"""torchcomms adapter, torchx component, failure injection, local orchestrator."""
+
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import threading
+import time
+from datetime import timedelta
+
+import pytest
+import torch
+import torch.distributed as dist
+from torch.distributed import PrefixStore, TCPStore
+
+from torchft_b200.failure import Failure, FailureInjector, send_failure
+from torchft_b200.process_group import FakeProcessGroupWrapper, ProcessGroupDummy
+from torchft_b200.torchcomms import ProcessGroupTorchComms
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Done:
+    def __init__(self, work=None):
+        self._w = work
+
+    def wait(self):
+        if self._w is not None:
+            self._w.wait()
+
+    def is_completed(self):
+        return self._w is None or self._w.is_completed()
+
+
+class _LoopbackComm:
+    """A reconfigurable communicator for the adapter test: one long-lived object whose
+    membership is swapped by reconfigure() (handles are ``host:port`` of a per-comm store)."""
+
+    def __init__(self):
+        self._store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
+        self._handle = f"127.0.0.1:{self._store.port}"
+        self._pg = None
+        self.reconfigures = 0
+        self.finalized = False
+
+    def get_backend(self):
+        return "loopback-gloo"
+
+    def get_device(self):
+        return torch.device("cpu")
+
+    def get_init_handle(self):
+        return self._handle
+
+    def reconfigure(self, uuid, init_handles, timeout):
+        rank = init_handles.index(self._handle)
+        host, port = init_handles[0].rsplit(":", 1)
+        root = self._store if rank == 0 else TCPStore(host, int(port), is_master=False, wait_for_workers=False)
+        self._pg = dist.ProcessGroupGloo(PrefixStore(f"q{uuid}", root), rank, len(init_handles), timeout)
+        self.reconfigures += 1
+        return _Done()
+
+    def finalize(self):
+        self.finalized = True
+        self._pg = None
+
+    def all_reduce(self, t, op, async_op=True):
+        o = dist.AllreduceOptions()
+        o.reduceOp = op
+        return _Done(self._pg.allreduce([t], o))
+
+    def broadcast(self, t, root, async_op=True):
+        o = dist.BroadcastOptions()
+        o.rootRank = root
+        return _Done(self._pg.broadcast([t], o))
+
+    def all_gather(self, outs, t, async_op=True):
+        return _Done(self._pg.allgather([outs], [t]))
+
+    def barrier(self, async_op=True):
+        return _Done(self._pg.barrier())
+
+    def send(self, t, dst, async_op=True):
+        return _Done(self._pg.send([t], dst, 0))
+
+    def recv(self, t, src, async_op=True):
+        return _Done(self._pg.recv([t], src, 0))
+
+
+def test_torchcomms_adapter_reconfigures_in_place():
+    store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
+    addr = f"127.0.0.1:{store.port}"
+    world = 2
+    comms = [_LoopbackComm() for _ in range(world)]
+    pgs = [ProcessGroupTorchComms(c, timeout=timedelta(seconds=20)) for c in comms]
+    out = [None] * world
+    errs = []
+
+    def run(rank):
+        try:
+            pg = pgs[rank]
+            for q in (1, 2):  # two quorums over the SAME communicator object
+                pg.configure(f"{addr}/tc/{q}", f"r{rank}", rank, world, quorum_id=q)
+                assert pg.size() == world
+                t = torch.full((4,), float(rank + 1))
+                pg.allreduce([t], dist.ReduceOp.SUM).wait()
+                assert t.tolist() == [3.0] * 4
+                b = torch.full((3,), float(rank))
+                o = dist.BroadcastOptions()
+                o.rootRank = 1
+                w = pg.broadcast([b], o)
+                w.wait()
+                assert w.get_future().value() == [b] and b.tolist() == [1.0] * 3
+                gathered = [torch.zeros(2) for _ in range(world)]
+                pg.allgather([gathered], [torch.full((2,), float(rank))], None).wait()
+                assert [g[0].item() for g in gathered] == [0.0, 1.0]
+                if rank == 0:
+                    pg.send([torch.arange(5.0)], 1, 0).wait()
+                else:
+                    r = torch.zeros(5)
+                    pg.recv([r], 0, 0).wait()
+                    assert r.tolist() == [0, 1, 2, 3, 4]
+                pg.barrier().wait()
+            out[rank] = comms[rank].reconfigures
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert not errs, errs
+    assert out == [2, 2]
+    assert pgs[0].getBackendName() == "torchcomms:loopback-gloo"
+    with pytest.raises(ValueError):
+        pgs[0].allreduce([torch.zeros(1), torch.zeros(1)], dist.ReduceOp.SUM)
+    pgs[0].abort()
+    assert comms[0].finalized
+    with pytest.raises(RuntimeError):
+        pgs[0].barrier()
+    pgs[1].shutdown()
+
+
+def test_torchx_component_spec_and_import_gate():
+    from torchft_b200 import torchx as tx
+
+    roles = tx.hsdp_spec("--lr", "1", replicas=3, workers_per_replica=2, script="train.py", gpus_per_node=8)
+    assert [r.name for r in roles] == [f"replica_group_{i}" for i in range(3)]
+    assert roles[2].env["REPLICA_GROUP_ID"] == "2" and roles[2].env["NUM_REPLICA_GROUPS"] == "3"
+    assert "--master_port=29602" in roles[2].args and roles[2].args[-3:] == ["train.py", "--lr", "1"]
+    assert roles[1].env["CUDA_VISIBLE_DEVICES"] == "2,3"
+    try:
+        import torchx  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            tx.hsdp(replicas=2)
+
+
+def test_failure_injector_comms_and_stall():
+    pg = FakeProcessGroupWrapper(ProcessGroupDummy(0, 1))
+    aborted = []
+    pg.abort = lambda: aborted.append(True)  # type: ignore[method-assign]
+    inj = FailureInjector(pg=pg).start()
+    try:
+        assert send_failure(inj.port, Failure.COMMS) == "ok"
+        deadline = time.time() + 5
+        while not aborted and time.time() < deadline:
+            time.sleep(0.01)
+        assert aborted
+        assert send_failure(inj.port, Failure.STALL_PEER) == "ok"
+        assert inj.stalled.wait(5)
+        t = threading.Thread(target=inj.maybe_stall, daemon=True)
+        t.start()
+        t.join(0.2)
+        assert t.is_alive()  # a stalled peer never proceeds
+        inj.stalled.clear()
+        t.join(2)
+        assert not t.is_alive()
+        # unknown commands are refused and do not kill the listener
+        import socket
+
+        with socket.create_connection(("127.0.0.1", inj.port), timeout=5) as s:
+            s.sendall(b"bogus\n")
+            assert b"unknown" in s.recv(64)
+    finally:
+        inj.stop()
+
+
+@pytest.mark.parametrize("kind,check", [("kill_proc", lambda rc: rc == 1), ("segfault", lambda rc: rc < 0)])
+def test_failure_injector_fatal_kinds(kind, check):
+    code = (
+        "import sys, time; sys.path.insert(0, %r)\n"
+        "from torchft_b200.failure import FailureInjector\n"
+        "inj = FailureInjector().start(); print(inj.port, flush=True); time.sleep(30)\n" % ROOT
+    )
+    p = subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    try:
+        port = int(p.stdout.readline())
+        send_failure(port, Failure(kind))
+        rc = p.wait(20)
+        assert check(rc), rc
+    finally:
+        if p.poll() is None:
+            p.kill()
+
+
+@pytest.mark.timeout(240)
+def test_orchestrator_runs_groups_to_completion(tmp_path):
+    env = dict(os.environ, USE_CPU="1", TRAIN_STEPS="12", CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run(
+        [sys.executable, os.path.join(ROOT, "examples/orchestrator/train_orchestrated.py"), "--replicas", "2",
+         "--min-replicas", "1", "--join-timeout-ms", "1000", "--log-dir", str(tmp_path), os.path.join(ROOT, "train_ddp.py")],
+        env=env, capture_output=True, text=True, timeout=220)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("finished") == 2, p.stdout
+    logs = "".join(open(os.path.join(tmp_path, f)).read() for f in os.listdir(tmp_path) if f.endswith(".log"))
+    assert '"final_step": 12' in logs

@@ -211,3 +211,38 @@ def test_direct_wgrad_into_flat_buffer_matches_accumulate_path():
         grads.append(flat.grad.float().clone())
     rel = (grads[0] - grads[1]).norm() / grads[0].norm()
     assert rel < 1e-2, rel
+
+
+@pytest.mark.parametrize("world_size", [2, 3, 8])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 0.05), (torch.bfloat16, 0.06), (torch.float16, 0.05)])
+@pytest.mark.parametrize("op", ["sum", "avg"])
+def test_q8_quantize_reduce_dequantize_all_views(K, world_size, dtype, tol, op):
+    """Single-device simulation of the quantised all-reduce over every 2-D view of the inputs
+    (strategy of the reference's quantization_test.py:38-106): every "rank" holds the same data,
+    so SUM must return world_size * x and AVG x."""
+    from torch.distributed import ReduceOp
+
+    from torchft_b200 import _test_utils
+    from torchft_b200 import quantization as Q
+
+    torch.manual_seed(11)
+    tensors_num, tensor_size = 3, 24
+    inp = (torch.rand(tensors_num * tensor_size, device="cuda") * 7.0 + 0.5).to(dtype)
+    rop = ReduceOp.SUM if op == "sum" else ReduceOp.AVG
+    splits = _test_utils.gen_splits(inp, tensor_size)
+    assert len(splits) == 7 ** 3
+    for split in splits[:: max(1, len(splits) // 24)]:
+        inputs, outputs = inp.clone(), torch.empty_like(inp)
+        ins = [c.view(*s) for s, c in zip(split, torch.split(inputs, tensor_size))]
+        outs = [c.view(*s) for s, c in zip(split, torch.split(outputs, tensor_size))]
+        quant = Q.fused_quantize_into_fp8(ins, world_size)
+        final = torch.empty_like(quant)
+        for rank in range(world_size):
+            copies = [quant.clone() for _ in range(world_size)]  # what rank would have received from every peer
+            Q.fused_reduce_fp8(ins, copies, world_size, rank, rop)
+            Q.copy_rank_slice(ins, final, copies[rank], world_size, rank)
+        Q.fused_dequantize_from_fp8(outs, final, world_size)
+        assert not _test_utils.any_nan(outs)
+        expect = inputs.float() * (world_size if op == "sum" else 1)
+        rel = ((outputs.float() - expect).abs() / (expect.abs() + 1e-7)).max().item()
+        assert rel < tol, (split, rel)

@@ -58,7 +58,7 @@ void xent_launch(void* logits, const void* target, float* loss, size_t rows, int
                  size_t row_stride, float grad_scale, long long ignore_index, cudaStream_t s);
 void adamw_launch(void* p, float* master, float* m, float* v, const void* g, size_t n, float lr,
                   float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
-                  const int* gate, cudaStream_t s);
+                  const int* gate, int max_blocks, cudaStream_t s);
 void sumsq_launch(const void* g, size_t n, float* out, cudaStream_t s);
 void heal_copy_launch(const void* table_dev, int nentries, size_t total_chunks, size_t chunk_bytes,
                       int blocks, cudaStream_t s);

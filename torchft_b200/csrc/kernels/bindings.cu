@@ -280,10 +280,12 @@ PYBIND11_MODULE(_K, m) {
   });
   m.def("adamw", [](uintptr_t p, uintptr_t master, uintptr_t mm, uintptr_t v, uintptr_t g, size_t n,
                     float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
-                    float gscale, uintptr_t gate, uintptr_t s) {
+                    float gscale, uintptr_t gate, uintptr_t s, int max_blocks) {
     adamw_launch(P<void>(p), P<float>(master), P<float>(mm), P<float>(v), P<void>(g), n, lr, b1, b2,
-                 eps, wd, bc1, bc2, gscale, P<const int>(gate), S(s));
-  });
+                 eps, wd, bc1, bc2, gscale, P<const int>(gate), max_blocks, S(s));
+  }, py::arg("p"), py::arg("master"), py::arg("m"), py::arg("v"), py::arg("g"), py::arg("n"), py::arg("lr"),
+     py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("bc1"), py::arg("bc2"),
+     py::arg("gscale"), py::arg("gate"), py::arg("stream"), py::arg("max_blocks") = 0);
   m.def("sumsq", [](uintptr_t g, size_t n, uintptr_t out, uintptr_t s) {
     sumsq_launch(P<void>(g), n, P<float>(out), S(s));
   });

@@ -488,9 +488,10 @@ void xent_launch(void* logits, const void* target, float* loss, size_t rows, int
 
 void adamw_launch(void* p, float* master, float* m, float* v, const void* g, size_t n, float lr,
                   float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
-                  const int* gate, cudaStream_t s) {
+                  const int* gate, int max_blocks, cudaStream_t s) {
   AdamArgs a{(bf16*)p, master, m, v, (const bf16*)g, n, lr, b1, b2, eps, wd, bc1, bc2, gscale, gate};
-  adamw_kernel<<<grid_for(n / 8 + 1, 512, 148 * 8), 512, 0, s>>>(a);
+  // max_blocks > 0 narrows the grid so the (HBM-bound) update can share the GPU with tensor-core work
+  adamw_kernel<<<grid_for(n / 8 + 1, 512, max_blocks > 0 ? max_blocks : 148 * 8), 512, 0, s>>>(a);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -115,3 +115,25 @@ def fused_reduce_fp8(inputs: List[torch.Tensor], all_buffers: List[torch.Tensor]
         ptrs = torch.tensor([b.data_ptr() + o for b in all_buffers], dtype=torch.int64, device=dev)
         K.q8_reduce(ptrs.data_ptr(), world_size, rank, t.numel(), post, all_buffers[rank].data_ptr() + o, sp)
 
+
+
+def rank_slice_views(inputs: Sequence[torch.Tensor], buf: torch.Tensor, world_size: int, rank: int) -> List[torch.Tensor]:
+    """uint8 views of the parts of a :func:`fused_quantize_into_fp8` buffer that rank ``rank`` owns:
+    per tensor, its run of fp32 scales and its run of 512-byte payload groups."""
+    K = _native.load()
+    offs, _ = _layout(inputs, world_size)
+    views = []
+    for t, o in zip(inputs, offs):
+        g = K.q8_ngroups(t.numel(), world_size)
+        sl = g // world_size
+        poff = (g * 4 + 15) & ~15
+        views.append(buf[o + rank * sl * 4: o + (rank + 1) * sl * 4])
+        views.append(buf[o + poff + rank * sl * GROUP: o + poff + (rank + 1) * sl * GROUP])
+    return views
+
+
+def copy_rank_slice(inputs: Sequence[torch.Tensor], dst: torch.Tensor, src: torch.Tensor, world_size: int, rank: int) -> None:
+    """``dst[slice of rank] = src[slice of rank]`` for every tensor region (the all-gather step of a
+    quantised all-reduce when it is emulated on one device, e.g. in tests)."""
+    for d, s in zip(rank_slice_views(inputs, dst, world_size, rank), rank_slice_views(inputs, src, world_size, rank)):
+        d.copy_(s)

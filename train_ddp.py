@@ -98,6 +98,11 @@ def main() -> None:
     ddp = DistributedDataParallel(manager, m)
     opt = Optimizer(manager, inner)
     crit = nn.CrossEntropyLoss()
+    injector = None
+    if os.environ.get("TORCHFT_FAILURE_PORT_FILE"):  # chaos testing (examples/orchestrator)
+        from torchft_b200.failure import FailureInjector
+
+        injector = FailureInjector(manager).start()
     print(m, f"{sum(p.numel() for p in m.parameters())} params", flush=True)
 
     epoch = 0
@@ -106,6 +111,8 @@ def main() -> None:
         epoch += 1
         for x, y in loader:
             x, y = x.to(device), y.to(device)
+            if injector is not None:
+                injector.maybe_stall()
             opt.zero_grad()       # starts the (async) quorum for this step
             loss = crit(ddp(x), y)
             loss.backward()       # gradients all-reduced across the live replica groups
