@@ -22,6 +22,39 @@ def test_ft_smoke_step_single_gpu():
     assert _native.kernel_launches() - before > 30  # native kernels actually ran
 
 
+def test_overlapped_optimizer_is_bit_identical_to_single_launch():
+    """Per-stage AdamW on the side stream (next forward gated stage by stage) must produce exactly
+    the parameters of the one-launch update."""
+    from datetime import timedelta
+
+    from torchft_b200.bench_utils import local_lighthouse, loopback
+    from torchft_b200.parallel.trainer import FaultTolerantTrainer
+
+    results = []
+    for overlap in (False, True):
+        lh = local_lighthouse()
+        tr = FaultTolerantTrainer("llama3_debug", loopback(lh.address()), replica_id=f"ovl_{int(overlap)}_0",
+                                  timeout=timedelta(seconds=30), bucket_mb=1.0, overlap_optimizer=overlap,
+                                  optimizer_blocks=7 if overlap else 0)
+        try:
+            g = torch.Generator().manual_seed(5)
+            losses = []
+            for _ in range(4):
+                tok = torch.randint(0, tr.cfg.vocab_size, (2, 128), generator=g).pin_memory()
+                tgt = torch.randint(0, tr.cfg.vocab_size, (2, 128), generator=g).pin_memory()
+                losses.append(tr.step(tok, tgt))
+            sd = tr.state_dict()  # joins the optimizer stream
+            torch.cuda.synchronize()
+            results.append((losses, sd["param"].clone(), sd["m"].clone(), sd["v"].clone()))
+            assert len(tr._opt_ranges if overlap else []) == (tr.cfg.n_layers + 2 if overlap else 0)
+        finally:
+            tr.shutdown()
+            lh.shutdown()
+    (l0, p0, m0, v0), (l1, p1, m1, v1) = results
+    assert l0 == l1
+    assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
+
+
 def test_graft_smoke_entry():
     sys.path.insert(0, ROOT)
     import __graft_entry__

@@ -109,6 +109,13 @@ class Llama(nn.Module):
         self.norm = nn.Parameter(torch.empty(cfg.dim, **kw))
         self.output = nn.Parameter(torch.empty(cfg.vocab_size, cfg.dim, **kw))
         self._cs: Optional[torch.Tensor] = None
+        # called with the stage index right before that stage's parameters are first read in forward
+        # (stage order = param_stages()); lets an optimizer that updates stage by stage gate the forward
+        self.stage_hook: Optional[Callable[[int], None]] = None
+
+    def param_stages(self) -> List[List[nn.Parameter]]:
+        """Parameters grouped by first use in forward: [embedding], one group per block, [final norm, output]."""
+        return [[self.tok_embeddings], *[list(b.parameters()) for b in self.layers], [self.norm, self.output]]
 
     @torch.no_grad()
     def init_weights(self, seed: int = 0) -> None:
@@ -131,8 +138,13 @@ class Llama(nn.Module):
     def hidden(self, tokens: torch.Tensor) -> torch.Tensor:
         B, S = tokens.shape
         cs = self.rope_cache(S, tokens.device)
+        hook = self.stage_hook
+        if hook is not None:
+            hook(0)
         x = F.embedding(tokens, self.tok_embeddings)
-        for blk in self.layers:
+        for i, blk in enumerate(self.layers):
+            if hook is not None:
+                hook(i + 1)
             if self.cfg.activation_checkpoint == "full" and torch.is_grad_enabled():
                 from torch.utils.checkpoint import checkpoint
 
@@ -145,6 +157,8 @@ class Llama(nn.Module):
         """Returns the mean next-token loss when ``targets`` is given, else logits."""
         x = self.hidden(tokens)
         B, S, d = x.shape
+        if self.stage_hook is not None:
+            self.stage_hook(len(self.layers) + 1)
         if targets is None:
             return fused.rmsnorm(x, self.norm, self.cfg.norm_eps) @ self.output.t()
         h = fused.rmsnorm(x, self.norm, self.cfg.norm_eps).view(B * S, d)

@@ -261,6 +261,25 @@ class FlatAdamW:
             grad_scale, gate.data_ptr() if gate is not None else 0, _native.stream_ptr(),
         )
 
+    def step_ranges(self, ranges, streams_events, grad_scale: float = 1.0, gate: Optional[torch.Tensor] = None,
+                    max_blocks: int = 0) -> None:
+        """The same update as :meth:`step`, cut into element ranges ``[(lo, hi), ...]`` that are launched
+        in the given order on ``stream``; ``events[i]`` is recorded after range ``i``. Lets the next
+        forward start on the first layers while the (HBM-bound) update of later layers is still running
+        underneath the (tensor-core-bound) GEMMs. ``streams_events`` = ``(stream, events)``."""
+        K = _native.load()
+        stream, events = streams_events
+        self.t += 1
+        lr = self.param_groups[0]["lr"]
+        b1, b2 = self.betas
+        bc1, bc2 = 1.0 - b1 ** self.t, 1.0 - b2 ** self.t
+        gp = gate.data_ptr() if gate is not None else 0
+        p, w, m, v, g = (t.data_ptr() for t in (self.p, self.master, self.m, self.v, self.g))
+        for (lo, hi), ev in zip(ranges, events):
+            K.adamw(p + 2 * lo, w + 4 * lo, m + 4 * lo, v + 4 * lo, g + 2 * lo, hi - lo, lr, b1, b2, self.eps,
+                    self.weight_decay, bc1, bc2, grad_scale, gp, stream.cuda_stream, max_blocks)
+            ev.record(stream)
+
     def grad_sumsq(self) -> torch.Tensor:
         K = _native.load()
         out = torch.zeros(1, dtype=torch.float32, device=self.g.device)
