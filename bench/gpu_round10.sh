@@ -7,6 +7,7 @@ echo "=== overlap probe"; timeout 300 python bench/overlap_probe.py > gpurun_out
 echo "=== bench 1 gpu (overlapped AdamW, default)"; timeout 600 python bench.py --gpus 1 --steps 6 --warmup 3 > gpurun_out/bench_n1_ovl.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_n1_ovl.log | cut -c1-330
 echo "=== bench 1 gpu (overlapped AdamW, 296 CTAs)"; TORCHFT_B200_OPT_BLOCKS=296 timeout 600 python bench.py --gpus 1 --steps 6 --warmup 3 > gpurun_out/bench_n1_ovl296.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_n1_ovl296.log | cut -c1-330
 echo "=== bench 1 gpu (single-launch AdamW)"; TORCHFT_B200_OVERLAP_OPT=0 timeout 600 python bench.py --gpus 1 --steps 6 --warmup 3 > gpurun_out/bench_n1_noovl.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/bench_n1_noovl.log | cut -c1-330
+echo "=== W=8 collectives, 8 ranks oversubscribed on this GPU"; timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29571 bench/comm_oversub.py > gpurun_out/comm_oversub_w8.log 2>&1; echo "rc=$?"; grep -E "COMM_OVERSUB|FAIL|Error" gpurun_out/comm_oversub_w8.log | head -8 | cut -c1-600
 echo "=== ncu adamw (current kernel)"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:adamw -c 1 -s 3 -f -o gpurun_out/prof_adamw_v2 python bench/kernel_micro.py --only adamw --iters 1 > gpurun_out/ncu_adamw_v2.log 2>&1; echo "ncu rc=$?"
 echo "=== diloco bench"; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29561 bench/diloco_bench.py > gpurun_out/diloco_bench.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/diloco_bench.log | cut -c1-400
