@@ -17,5 +17,6 @@ except Exception as e:
     print('no comm json', e)
 PY
 tail -5 gpurun_out/comm_bench_vmm_w$N.log | cut -c1-300
+echo "=== multi-GPU tests (HSDP/FSDP2 4 GPUs, quantized collectives + Baby NCCL 2 GPUs, FT step)"; timeout 600 python -m pytest tests/test_hsdp_gpu.py tests/test_ft_gpu.py tests/test_kernels_gpu.py -m gpu -q --timeout 500 > gpurun_out/pytest_gpu_multi.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu_multi.log | cut -c1-300
 echo "=== bench $N gpu nccl-equivalent"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 6 --warmup 3 --impl nccl > gpurun_out/bench_n${N}_nccl.log 2>&1; echo "rc=$?"; grep '^{"metric' gpurun_out/bench_n${N}_nccl.log | cut -c1-400
 echo "=== comm tune $N gpus"; timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench/comm_tune.py --out gpurun_out/comm_tune_w$N.json > gpurun_out/comm_tune_w$N.log 2>&1; echo "rc=$?"; grep '^{"bytes' gpurun_out/comm_tune_w$N.log | cut -c1-300

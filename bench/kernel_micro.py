@@ -109,6 +109,8 @@ def main() -> None:
         m = torch.zeros(n, device=dev)
         v = torch.zeros(n, device=dev)
         record("adamw", timeit(lambda: K.adamw(p.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), n, 1e-3, 0.9, 0.95, 1e-8, 0.1, 0.1, 0.05, 1.0, 0, sp()), args.iters, flush), n * 28)
+        for cap in (148, 296, 592, 1184, 2368):  # CTA-cap sweep (default = 4 CTAs/SM)
+            record(f"adamw_cap{cap}", timeit(lambda: K.adamw(p.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), n, 1e-3, 0.9, 0.95, 1e-8, 0.1, 0.1, 0.05, 1.0, 0, sp(), cap), args.iters, flush), n * 28)
         del p, g, master, m, v
     if want("q8"):
         n = 1 << 28

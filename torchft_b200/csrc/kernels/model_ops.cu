@@ -490,8 +490,9 @@ void adamw_launch(void* p, float* master, float* m, float* v, const void* g, siz
                   float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
                   const int* gate, int max_blocks, cudaStream_t s) {
   AdamArgs a{(bf16*)p, master, m, v, (const bf16*)g, n, lr, b1, b2, eps, wd, bc1, bc2, gscale, gate};
-  // max_blocks > 0 narrows the grid so the (HBM-bound) update can share the GPU with tensor-core work
-  adamw_kernel<<<grid_for(n / 8 + 1, 512, max_blocks > 0 ? max_blocks : 148 * 8), 512, 0, s>>>(a);
+  // 4 CTAs/SM measured best (bench/overlap_probe.py: 8.9 ms vs 10.6 ms at 8/SM for 8 x 218 M params);
+  // max_blocks > 0 overrides
+  adamw_kernel<<<grid_for(n / 8 + 1, 512, max_blocks > 0 ? max_blocks : 148 * 4), 512, 0, s>>>(a);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 
