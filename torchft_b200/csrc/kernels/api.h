@@ -49,7 +49,7 @@ void rmsnorm_fwd_launch(const void* x, const void* w, void* y, float* rstd, int 
 int rmsnorm_bwd_grid(int rows);
 void rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                         float* dw_partial, void* dw, int accumulate, int rows, int H,
-                        cudaStream_t s);
+                        cudaStream_t s, const void* dres = nullptr);
 void swiglu_fwd_launch(const void* gu, void* y, size_t T, int F, cudaStream_t s);
 void swiglu_bwd_launch(const void* dy, const void* gu, void* dgu, size_t T, int F, cudaStream_t s);
 void rope_launch(const void* in, void* out, const void* cs, size_t T, int S, int heads, int D,

@@ -259,10 +259,11 @@ PYBIND11_MODULE(_K, m) {
   m.def("rmsnorm_bwd_grid", &rmsnorm_bwd_grid);
   m.def("rmsnorm_bwd", [](uintptr_t dy, uintptr_t x, uintptr_t w, uintptr_t rstd, uintptr_t dx,
                           uintptr_t dw_partial, uintptr_t dw, bool accumulate, int rows, int H,
-                          uintptr_t s) {
+                          uintptr_t s, uintptr_t dres) {
     rmsnorm_bwd_launch(P<void>(dy), P<void>(x), P<void>(w), P<float>(rstd), P<void>(dx),
-                       P<float>(dw_partial), P<void>(dw), accumulate ? 1 : 0, rows, H, S(s));
-  });
+                       P<float>(dw_partial), P<void>(dw), accumulate ? 1 : 0, rows, H, S(s), P<void>(dres));
+  }, py::arg("dy"), py::arg("x"), py::arg("w"), py::arg("rstd"), py::arg("dx"), py::arg("dw_partial"),
+     py::arg("dw"), py::arg("accumulate"), py::arg("rows"), py::arg("H"), py::arg("stream"), py::arg("dres") = 0);
   m.def("swiglu_fwd", [](uintptr_t gu, uintptr_t y, size_t T, int F, uintptr_t s) {
     swiglu_fwd_launch(P<void>(gu), P<void>(y), T, F, S(s));
   });

@@ -61,12 +61,14 @@ __global__ void __launch_bounds__(512) rmsnorm_fwd_kernel(const bf16* __restrict
   }
 }
 
-// dx = rstd * (dy*w - xhat * mean(dy*w*xhat)); dw_partial[block] += dy * xhat
+// dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) (+ dres); dw_partial[block] += dy * xhat
+// dres (optional) is the gradient arriving over the residual connection that bypasses the norm:
+// adding it here saves the separate elementwise accumulation pass autograd would run.
 template <int NV>
 __global__ void __launch_bounds__(512) rmsnorm_bwd_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
     const float* __restrict__ rstd, bf16* __restrict__ dx, float* __restrict__ dw_partial,
-    int rows, int H) {
+    const bf16* __restrict__ dres, int rows, int H) {
   __shared__ float red[32];
   const int nvec = H / 8;
   float dw[NV][8];
@@ -106,6 +108,12 @@ __global__ void __launch_bounds__(512) rmsnorm_bwd_kernel(
         float o[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = r * (g[i][k] - xh[i][k] * dot);
+        if (dres != nullptr) {
+          float rf[8];
+          P8::unpack(ld_stream(dres + (size_t)row * H + v * 8), rf);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += rf[k];
+        }
         st_stream(dx + (size_t)row * H + v * 8, P8::pack(o));
       }
     }
@@ -440,19 +448,19 @@ int rmsnorm_bwd_grid(int rows) { return rows < 296 ? rows : 296; }
 
 void rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                         float* dw_partial, void* dw, int accumulate, int rows, int H,
-                        cudaStream_t s) {
+                        cudaStream_t s, const void* dres) {
   if (H % 8 || H > 8 * kRmsMaxVec * 512) throw std::runtime_error("rmsnorm: H must be %8 and <= 16384");
   const int grid = rmsnorm_bwd_grid(rows);
   const int nv = (H / 8 + 511) / 512;
   if (nv <= 1)
     rmsnorm_bwd_kernel<1><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
-                                               (bf16*)dx, dw_partial, rows, H);
+                                               (bf16*)dx, dw_partial, (const bf16*)dres, rows, H);
   else if (nv <= 2)
     rmsnorm_bwd_kernel<2><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
-                                               (bf16*)dx, dw_partial, rows, H);
+                                               (bf16*)dx, dw_partial, (const bf16*)dres, rows, H);
   else
     rmsnorm_bwd_kernel<4><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
-                                               (bf16*)dx, dw_partial, rows, H);
+                                               (bf16*)dx, dw_partial, (const bf16*)dres, rows, H);
   colsum_kernel<<<(H + 255) / 256, 256, 0, s>>>(dw_partial, grid, H, (bf16*)dw, accumulate);
   TFT_CUDA_CHECK(cudaGetLastError());
 }

@@ -87,16 +87,18 @@ class Block(nn.Module):
     def forward(self, x: torch.Tensor, cs: torch.Tensor) -> torch.Tensor:
         cfg = self.cfg
         B, S, d = x.shape
-        qkv = fused.norm_linear(x, self.attention_norm, self.wqkv, cfg.norm_eps)
+        # residual stream is threaded through the norm nodes (norm_linear_res) and added in the
+        # projection GEMMs' epilogues: no standalone elementwise add in forward or backward
+        x, qkv = fused.norm_linear_res(x, self.attention_norm, self.wqkv, cfg.norm_eps)
         q, k, v = fused.rope_qkv(qkv.view(B * S, -1), cs, B, S, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim)
         o = F.scaled_dot_product_attention(
             q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True,
             enable_gqa=cfg.n_kv_heads != cfg.n_heads,
         )
         o = o.transpose(1, 2).reshape(B, S, d)
-        h = x + fused.linear(o, self.wo)
-        gu = fused.norm_linear(h, self.ffn_norm, self.w13, cfg.norm_eps)
-        return h + fused.swiglu_linear(gu, self.w2)
+        h = fused.linear(o, self.wo, res=x)
+        h, gu = fused.norm_linear_res(h, self.ffn_norm, self.w13, cfg.norm_eps)
+        return fused.swiglu_linear(gu, self.w2, res=h)
 
 
 class Llama(nn.Module):
