@@ -255,7 +255,7 @@ def main() -> None:
                 "global_batch": B * world,
                 "seq_len": S,
                 "parallelism": f"ft-hsdp: {world} replica group(s) x 1 GPU (shard degree 1), fault-tolerant DP over NVLink",
-                "optimizer": "AdamW (fp32 master/m/v), single fused launch, gated on should_commit",
+                "optimizer": "AdamW (fp32 master/m/v), applied only after should_commit; one launch per forward stage on a side stream so the next forward overlaps the update" if getattr(trainer, "_opt_stream", None) is not None else "AdamW (fp32 master/m/v), single fused launch after should_commit",
                 "activation_checkpoint": ac or cfg.activation_checkpoint,
                 "grad_allreduce": "fused P2P kernel, zero-copy symmetric buckets, overlapped with backward" if args.impl == "native" else "NCCL allreduce SUM + div",
                 "quantized_allreduce": bool(args.quantize),

@@ -118,3 +118,22 @@ def test_quantized_collectives_and_baby_nccl_two_gpus():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"failures": 0' in r.stdout
+
+
+def test_stream_timeout_fires_only_on_a_stuck_stream():
+    import threading
+    import time
+    from datetime import timedelta
+
+    from torchft_b200.futures import stream_timeout
+
+    late = threading.Event()
+    torch.cuda._sleep(int(3e9))  # > 1 s of device time
+    stream_timeout(late.set, timedelta(milliseconds=100))
+    assert late.wait(3.0)
+    torch.cuda.synchronize()
+    fine = threading.Event()
+    torch.ones(8, device="cuda").sum()
+    stream_timeout(fine.set, timedelta(milliseconds=200))
+    time.sleep(0.6)
+    assert not fine.is_set()
