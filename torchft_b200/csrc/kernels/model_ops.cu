@@ -498,9 +498,10 @@ void adamw_launch(void* p, float* master, float* m, float* v, const void* g, siz
                   float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
                   const int* gate, int max_blocks, cudaStream_t s) {
   AdamArgs a{(bf16*)p, master, m, v, (const bf16*)g, n, lr, b1, b2, eps, wd, bc1, bc2, gscale, gate};
-  // 4 CTAs/SM measured best (bench/overlap_probe.py: 8.9 ms vs 10.6 ms at 8/SM for 8 x 218 M params);
-  // max_blocks > 0 overrides
-  adamw_kernel<<<grid_for(n / 8 + 1, 512, max_blocks > 0 ? max_blocks : 148 * 4), 512, 0, s>>>(a);
+  // CTA-cap sweep at 1 Gi params (profiles/kernel_micro_adamw_caps.json): 148 -> 0.83, 592 -> 0.82,
+  // 1184 -> 0.89, 2368 -> 0.92 of measured HBM bandwidth: many short CTAs keep both resident slots of
+  // every SM refilled. max_blocks > 0 overrides.
+  adamw_kernel<<<grid_for(n / 8 + 1, 512, max_blocks > 0 ? max_blocks : 148 * 16), 512, 0, s>>>(a);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 

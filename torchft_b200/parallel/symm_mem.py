@@ -106,7 +106,10 @@ class SymmetricComm:
         # "vmm": cuMemCreate-backed segments (survive exporter death, NVLS-capable); "ipc": cudaMalloc + cudaIpc
         self._mode = os.environ.get("TORCHFT_B200_SYMM", "ipc")
         self._nvls_enabled = os.environ.get("TORCHFT_B200_NVLS", "1") != "0"
-        self._nvls_min = int(os.environ.get("TORCHFT_B200_NVLS_MIN_KB", "512")) << 10
+        # NVLS threshold; None = pick by world size at configure() (see _default_nvls_min)
+        env_nvls = os.environ.get("TORCHFT_B200_NVLS_MIN_KB")
+        self._nvls_min_env: Optional[int] = (int(env_nvls) << 10) if env_nvls is not None else None
+        self._nvls_min = self._nvls_min_env if self._nvls_min_env is not None else (1 << 62)
         self._fdserver: Any = None
         self._peer_vmm: Dict[Tuple[str, int, str], Tuple[int, int, int]] = {}  # (host, pid, seg) -> (va, handle, size)
         self._mc: Dict[str, Tuple[int, int, int]] = {}  # segment -> (mc handle, multicast va, size)
@@ -252,6 +255,7 @@ class SymmetricComm:
                 floor = max(int(d["floor"]) for d in descs)
                 self._flag = max(floor, int(epoch) << 32) + 16
                 self._rank, self._world, self._epoch = rank, world, int(epoch)
+                self._nvls_min = self._nvls_min_env if self._nvls_min_env is not None else self._default_nvls_min(world)
                 if self._mode == "vmm" and self._nvls_enabled and world > 1 and K.multicast_supported():
                     self._setup_multicast(store, descs, [n for n in names if n != "core"], rank, world)
                 self._configured = True
@@ -310,13 +314,20 @@ class SymmetricComm:
         if self._force_plan is not None:
             return self._force_plan
         w = max(self._world, 2)
-        oneshot_max = self._oneshot_max * (8 if w == 2 else (4 if w <= 4 else 2))
+        oneshot_max = self._oneshot_max * (8 if w == 2 else (4 if w <= 4 else 1))  # W=8: two-shot wins from 256 KB
         if nbytes <= oneshot_max:
             blocks = max(1, min(128, (nbytes + (16 << 10) - 1) // (16 << 10)))
             if (nbytes + blocks - 1) // blocks <= (64 << 10):
                 return 0, blocks
         blocks = max(8, min(self._max_blocks, nbytes // (64 << 10)))
         return 1, blocks
+
+    @staticmethod
+    def _default_nvls_min(world: int) -> int:
+        """In-switch reduction moves ~(1 + 1/N)·S per link direction, the P2P two-shot 2(N-1)/N·S: equal at
+        N=4 (measured: no gain), 1.5x worse at N=2 (measured 2.71 vs 1.67 ms per GiB), 1.3x better at N=8
+        (measured 2.28 vs 2.98 ms per GiB, ahead from 256 KB; profiles/comm_bench_vmm_nvls_8gpu.json)."""
+        return (256 << 10) if world >= 5 else (1 << 62)
 
     def _next_flag(self) -> int:
         f = self._flag

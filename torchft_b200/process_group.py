@@ -484,6 +484,36 @@ class ProcessGroupNCCL(ProcessGroupWrapper):
         pg._register_backend(torch.device("cuda"), BaseProcessGroup.BackendType.NCCL, backend)
         return pg
 
+    def alltoall_base(self, output_buffer: torch.Tensor, input_buffer: torch.Tensor, output_split_sizes: List[int],
+                      input_split_sizes: List[int], opts: Any) -> Work:
+        """All-to-all as ONE coalesced group of send/recv.
+
+        torch's NCCL all-to-all helper ends its group without the non-blocking retry loop, so on the
+        non-blocking communicators this class creates it fails with ``ncclInProgress`` ("NCCL Error 7",
+        seen on NCCL 2.28 / torch 2.11); the coalescing path of ``ProcessGroupNCCL`` polls correctly.
+        """
+        pg = self.parent
+        world, rank = pg.size(), pg.rank()
+
+        def cut(buf: torch.Tensor, sizes: List[int]) -> List[torch.Tensor]:
+            if sizes:
+                return list(torch.split(buf, list(sizes), dim=0))
+            if buf.shape[0] % world:
+                raise ValueError("alltoall_base: dim 0 must divide evenly by the world size")
+            return list(torch.split(buf, buf.shape[0] // world, dim=0))
+
+        ins, outs = cut(input_buffer, input_split_sizes), cut(output_buffer, output_split_sizes)
+        dev = input_buffer.device
+        with self._run_context():
+            outs[rank].copy_(ins[rank])
+            pg._start_coalescing(dev)
+            for p in range(world):
+                if p != rank:
+                    pg.send([ins[p]], p, 0)
+                    pg.recv([outs[p]], p, 0)
+            work = pg._end_coalescing(dev)
+        return self._wrap_work(work, self._opts_hook(opts))
+
     def abort(self, errored: bool = True) -> None:
         if os.environ.get(TRIGGER_FR_ON_ABORT_ENV, "false") == "true":
             trigger_nccl_fr_trace_through_pipe(dist.get_rank() if dist.is_initialized() else 0)
