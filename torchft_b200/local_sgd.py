@@ -201,6 +201,39 @@ class _StreamingDiLoCoFragment:
             if self._pin_memory and t.device.type == "cpu" and torch.cuda.is_available():
                 t = t.pin_memory()
             self.original_parameters[name] = t
+        # persistent pseudo-gradient buffers in NVLink-symmetric memory (zero-copy / in-switch all-reduce)
+        self._symm_flat: Dict[Tuple[torch.dtype, torch.device], torch.Tensor] = {}
+        self._alloc_symmetric_buffers()
+
+    def _group_sizes(self) -> Dict[Tuple[torch.dtype, torch.device], List[int]]:
+        groups: Dict[Tuple[torch.dtype, torch.device], List[int]] = {}
+        for i, p in enumerate(self._params):
+            lp = _local_view(p.data)
+            groups.setdefault((lp.dtype, lp.device), []).append(i)
+        return groups
+
+    def _alloc_symmetric_buffers(self) -> None:
+        """When the manager's process group owns peer-visible memory (ProcessGroupB200), place the flat
+        pseudo-gradient buffer there ONCE: every sync then reduces it in place (P2P or NVLS kernel)
+        instead of bouncing through the staging buffer, and nothing is allocated per sync. Must run
+        before the first quorum (segments are exchanged at configure time); replicas construct DiLoCo
+        identically, so names and sizes match."""
+        alloc = getattr(self._manager, "alloc_symmetric", None)
+        if alloc is None:
+            return
+        for gi, ((dt, dev), idxs) in enumerate(self._group_sizes().items()):
+            if dev.type != "cuda":
+                continue
+            total = sum((_local_view(self._params[i].data).numel() + 7) // 8 * 8 for i in idxs)
+            try:
+                buf = alloc(f"diloco_f{self._fragment_id}_g{gi}", total * torch.empty(0, dtype=dt).element_size())
+            except Exception:  # noqa: BLE001 - e.g. group already configured: fall back to plain buffers
+                logger.exception("symmetric pseudo-gradient buffer unavailable; using the staged path")
+                continue
+            if isinstance(buf, torch.Tensor) and buf.device == dev:
+                flat = buf.view(dt)[:total]
+                flat.zero_()  # alignment padding must stay finite (fp8 groups share a scale)
+                self._symm_flat[(dt, dev)] = flat
 
     # --------------------------------------------------------------- heal hooks
     def register_state_dict_fn(self) -> None:
@@ -258,17 +291,17 @@ class _StreamingDiLoCoFragment:
         """
         self._grads = {}
         self._flat_grads = []
-        groups: Dict[Tuple[torch.dtype, torch.device], List[int]] = {}
+        groups = self._group_sizes()
         locals_ = [_local_view(p.data) for p in self._params]
-        for i, lp in enumerate(locals_):
-            groups.setdefault((lp.dtype, lp.device), []).append(i)
         fused = self.should_quantize and self._manager.supports_fused_delta()
         for (dt, dev), idxs in groups.items():
             sizes = [(locals_[i].numel() + 7) // 8 * 8 for i in idxs]  # 16 B aligned slices
             total = sum(sizes)
             # flat_grad starts out holding the ORIGINAL weights on the fused path (the kernel
             # computes original - local on the fly and overwrites it with the averaged result)
-            flat_grad = torch.zeros(total, dtype=dt, device=dev)
+            flat_grad = self._symm_flat.get((dt, dev))
+            if flat_grad is None or flat_grad.numel() != total:
+                flat_grad = torch.zeros(total, dtype=dt, device=dev)
             flat_local = torch.zeros(total, dtype=dt, device=dev) if fused else None
             bounds: List[Tuple[int, int]] = []
             off = 0

@@ -352,6 +352,13 @@ class Manager:
             return pg.allreduce_q8(tensor, tensor, None, scale=scale, contribute=participating)  # type: ignore[attr-defined]
         return fused(tensor, op=ops[reduce_op], scale=scale, contribute=participating)
 
+    def alloc_symmetric(self, name: str, nbytes: int) -> Optional[torch.Tensor]:
+        """Peer-visible buffer from the process group (``ProcessGroupB200.alloc_symmetric``) or ``None``
+        when the group has no such memory. Tensors carved from it are all-reduced in place, zero-copy.
+        Call with identical arguments on every replica before the next quorum."""
+        fn = getattr(self._pg, "alloc_symmetric", None)
+        return fn(name, nbytes) if callable(fn) else None
+
     def supports_fused_delta(self) -> bool:
         """True when ``allreduce_delta`` runs as ONE fused kernel (ProcessGroupB200)."""
         return hasattr(self._pg, "allreduce_q8") and torch.cuda.is_available()

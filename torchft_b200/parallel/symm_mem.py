@@ -157,8 +157,11 @@ class SymmetricComm:
             self._ensure_core()
             if name in self._segments:
                 raise ValueError(f"symmetric segment {name!r} already exists")
+            if self._configured:
+                # peers learn about segments at configure(); adding one now would leave this rank
+                # unusable until the NEXT quorum change, so refuse loudly instead
+                raise RuntimeError("allocate symmetric segments before the group is configured (before the first quorum)")
             seg = self._alloc_segment(name, nbytes)
-            self._configured = self._configured and self._world == 1
             return seg.tensor[:nbytes]
 
     def set_timeout(self, timeout: timedelta) -> None:
