@@ -409,3 +409,15 @@ def test_dashboard_http(lighthouse):
     assert "dash" in status and "Step: 4" in status and "Heartbeats" in status
     with pytest.raises(urllib.error.HTTPError):
         urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{port}/replica/nobody/kill", method="POST"))
+
+
+def test_native_selftest_binary():
+    """The C++ control plane's own unit + integration tests (the reference runs `cargo test`)."""
+    import subprocess
+
+    from torchft_b200 import _build
+
+    exe = _build.build_selftest()
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed" in r.stdout

@@ -147,12 +147,31 @@ def build_lighthouse_binary(force: bool = False) -> Path:
     return out
 
 
+def build_selftest(force: bool = False) -> Path:
+    """Native unit/integration tests of the control plane (`cargo test` equivalent): bin/torchft_b200_selftest."""
+    cdir = CSRC / "control"
+    out = ROOT.parent / "bin" / "torchft_b200_selftest"
+    srcs = [cdir / f"{n}.cc" for n in ("wire", "quorum", "rpc", "lighthouse", "manager_server")] + [cdir / "tests" / "selftest.cc"]
+    flags = ["-O1", "-g", "-std=c++17", "-pthread"]
+    stamp_file = BUILD / "selftest_bin.stamp"
+    stamp = _stamp(srcs + sorted(cdir.glob("*.h")), flags)
+    if not force and out.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return out
+    out.parent.mkdir(parents=True, exist_ok=True)
+    BUILD.mkdir(parents=True, exist_ok=True)
+    _run([CXX] + flags + [f"-I{cdir}"] + [str(s) for s in srcs] + ["-o", str(out)])
+    stamp_file.write_text(stamp)
+    return out
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     BUILD.mkdir(parents=True, exist_ok=True)
     build_control(force=force)
     build_kernels(force=force, verbose=verbose)
     if (CSRC / "control" / "main" / "lighthouse_main.cpp").exists():
         build_lighthouse_binary(force=force)
+    if (CSRC / "control" / "tests" / "selftest.cc").exists():
+        build_selftest(force=force)
 
 
 if __name__ == "__main__":
