@@ -17,12 +17,14 @@ from __future__ import annotations
 import argparse
 import os
 import random
-import signal
+import re
 import subprocess
 import sys
 import tempfile
 import time
 from typing import Dict, List, Optional
+
+import psutil
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
@@ -37,6 +39,7 @@ class Group:
     def __init__(self, role: Role, port_file: str, log_dir: str) -> None:
         self.role, self.port_file, self.log_dir = role, port_file, log_dir
         self.proc: Optional[subprocess.Popen] = None
+        self._stragglers: List[psutil.Process] = []
         self.launches = 0
         self.died_at: Optional[float] = None
 
@@ -56,9 +59,43 @@ class Group:
         return self.proc is not None and self.proc.poll() is None
 
     def kill(self) -> None:
-        if self.alive():
-            assert self.proc is not None
-            os.killpg(self.proc.pid, signal.SIGKILL)  # exact process group we created
+        """SIGKILL the launcher AND its workers. torchrun puts every worker in its own session, so killing
+        the launcher's process group alone would orphan them; walk the exact process tree we started instead."""
+        if self.proc is None:
+            return
+        victims = []
+        try:
+            root = psutil.Process(self.proc.pid)
+            victims = root.children(recursive=True) + [root]
+        except psutil.NoSuchProcess:
+            pass
+        victims += self._stragglers
+        for v in victims:
+            try:
+                v.kill()
+            except psutil.NoSuchProcess:
+                pass
+        self._stragglers = []
+
+    def remember_workers(self) -> None:
+        """Record the live worker processes so that they can still be reaped after the launcher died
+        (a worker that os._exit()s takes the launcher down; a hung sibling would otherwise survive)."""
+        if self.proc is None:
+            return
+        try:
+            self._stragglers = psutil.Process(self.proc.pid).children(recursive=True)
+        except psutil.NoSuchProcess:
+            pass
+
+    def logged_step(self) -> int:
+        """Highest `step=N` in the current launch's log (the training scripts print one every few steps)."""
+        try:
+            with open(os.path.join(self.log_dir, f"{self.role.name}.{self.launches - 1}.log"), errors="replace") as f:
+                f.seek(max(0, os.path.getsize(f.name) - 4096))
+                steps = re.findall(r"step=(\d+)", f.read())
+            return int(steps[-1]) if steps else 0
+        except (OSError, ValueError):
+            return 0
 
     def injector_port(self) -> Optional[int]:
         try:
@@ -78,6 +115,9 @@ def main() -> None:
     ap.add_argument("--mtbf-secs", type=float, default=0.0, help="mean time between injected failures (0 = none)")
     ap.add_argument("--failures", default="kill_proc,segfault,comms,kill_group",
                     help="comma list from: " + ",".join([f.value for f in Failure] + [OUTSIDE_KILL]))
+    ap.add_argument("--stop-injecting-at-step", type=int, default=0,
+                    help="no more failures once any group logged `step=N` with N >= this (0 = never stop); lets a soak "
+                         "end with all groups in one quorum so their final weights can be compared")
     ap.add_argument("--relaunch-delay", type=float, default=2.0)
     ap.add_argument("--duration", type=float, default=0.0, help="stop after this many seconds (0 = until all groups exit 0)")
     ap.add_argument("--log-dir", default=None)
@@ -107,6 +147,8 @@ def main() -> None:
             time.sleep(0.5)
             now = time.monotonic()
             for g in groups:
+                if g.role.name not in done and g.alive():
+                    g.remember_workers()
                 if g.role.name in done or g.alive():
                     continue
                 assert g.proc is not None
@@ -117,12 +159,17 @@ def main() -> None:
                     g.died_at = now
                     print(f"{g.role.name} died rc={g.proc.returncode}; relaunch in {a.relaunch_delay}s", flush=True)
                 elif now - g.died_at >= a.relaunch_delay:
+                    g.kill()  # reap any worker that outlived its launcher
                     g.start()
                     print(f"{g.role.name} relaunched (launch #{g.launches})", flush=True)
             if len(done) == len(groups) or (a.duration and now - t0 >= a.duration):
                 break
             if now >= next_failure:
                 next_failure = now + rng.expovariate(1.0 / a.mtbf_secs)
+                if a.stop_injecting_at_step and max(g.logged_step() for g in groups) >= a.stop_injecting_at_step:
+                    next_failure = float("inf")
+                    print(f"[{now - t0:7.1f}s] step {a.stop_injecting_at_step} reached: no more failures", flush=True)
+                    continue
                 victims = [g for g in groups if g.alive() and g.role.name not in done]
                 if len(victims) <= a.min_replicas:  # never take the job below its quorum floor
                     continue

@@ -215,3 +215,19 @@ def test_orchestrator_runs_groups_to_completion(tmp_path):
     assert p.stdout.count("finished") == 2, p.stdout
     logs = "".join(open(os.path.join(tmp_path, f)).read() for f in os.listdir(tmp_path) if f.endswith(".log"))
     assert '"final_step": 12' in logs
+
+
+@pytest.mark.timeout(280)
+def test_chaos_soak_ends_with_identical_weights(tmp_path):
+    """Orchestrator + failure injection (kills from outside, in-process exit, comm aborts) over the CPU data plane:
+    every group must finish at the target step with bit-identical weights."""
+    import json
+
+    out = tmp_path / "soak.json"
+    env = dict(os.environ, USE_CPU="1", CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench/chaos_soak.py"), "--steps", "400", "--mtbf-secs", "6",
+                        "--failures", "kill_proc,comms,kill_group", "--timeout", "240", "--out", str(out)],
+                       env=env, capture_output=True, text=True, timeout=270)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    res = json.loads(out.read_text())
+    assert res["pass"] and res["final_weights_identical"] and res["n_injected"] >= 1, res

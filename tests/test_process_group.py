@@ -110,7 +110,7 @@ def test_gloo_world1_apis():
     pg.configure(f"127.0.0.1:{store.port}/a/1", "r0", 0, 1)
     assert pg.parent is not inner
     pg.shutdown()
-    with pytest.raises(AssertionError):
+    with pytest.raises(RuntimeError, match="not initialized"):
         pg.parent
 
 

@@ -252,7 +252,8 @@ class ProcessGroupWrapper(ProcessGroup):
 
     @property
     def parent(self) -> BaseProcessGroup:
-        assert self._pg is not None, "process group not initialized"
+        if self._pg is None:  # after abort() the group stays unusable until the next configure()
+            raise RuntimeError("process group not initialized (or aborted)")
         return self._pg
 
     def getBackendName(self) -> str:

@@ -57,7 +57,7 @@ def main() -> None:
     num_groups = int(os.environ.get("NUM_REPLICA_GROUPS", 2))
     total_steps = int(os.environ.get("TRAIN_STEPS", 50))
     min_replicas = int(os.environ.get("MIN_REPLICAS", 1))
-    out_path = os.environ.get("TRAIN_OUT", "")
+    out_path = os.environ.get("TRAIN_OUT", "").replace("{group}", str(replica_group))  # one file per replica group
     use_cuda = torch.cuda.is_available() and os.environ.get("USE_CPU", "0") != "1"
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", replica_group % max(torch.cuda.device_count(), 1)))) if use_cuda else torch.device("cpu")
     if use_cuda:
