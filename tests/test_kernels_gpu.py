@@ -248,3 +248,31 @@ def test_q8_quantize_reduce_dequantize_all_views(K, world_size, dtype, tol, op):
         # be off by 2^-4 per quantisation and the pipeline quantises twice)
         err = (outputs.float() - expect).abs() / (expect.abs() + 1e-7)
         assert err.mean().item() < tol and err.max().item() < 0.14, (split, err.mean().item(), err.max().item())
+
+
+def test_p2p_transport_inplace_targets_matched_by_key_path(K):
+    """Heal into a replica whose state_dict is structurally smaller than the sender's (fresh torch optimizer:
+    no per-parameter state yet): matching leaves are filled IN PLACE, the rest is allocated."""
+    from datetime import timedelta
+
+    from torchft_b200.checkpointing import P2PTransport
+
+    torch.manual_seed(9)
+    w_src, m_src = torch.randn(1000, device="cuda"), torch.randn(1000, device="cuda")
+    sender_sd = {"model": {"w": w_src}, "optim": {"state": {0: {"exp_avg": m_src, "step": torch.tensor(7.0)}}, "param_groups": [{"lr": 0.1}]}}
+    w_dst = torch.zeros(1000, device="cuda")
+    fresh_sd = {"model": {"w": w_dst}, "optim": {"state": {}, "param_groups": [{"lr": 0.5}]}}
+    t = timedelta(seconds=10)
+    src, dst = P2PTransport(t), P2PTransport(t, state_dict=lambda: fresh_sd)
+    try:
+        src.send_checkpoint([1], 3, sender_sd, t)
+        got = dst.recv_checkpoint(0, src.metadata(), 3, t)
+        torch.cuda.synchronize()
+        assert got["model"]["w"].data_ptr() == w_dst.data_ptr() and torch.equal(w_dst, w_src)
+        assert torch.equal(got["optim"]["state"][0]["exp_avg"], m_src)
+        assert got["optim"]["state"][0]["exp_avg"].data_ptr() != m_src.data_ptr()
+        assert float(got["optim"]["state"][0]["step"]) == 7.0 and got["optim"]["param_groups"][0]["lr"] == 0.1
+        src.disallow_checkpoint()
+    finally:
+        src.shutdown()
+        dst.shutdown()

@@ -224,11 +224,18 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
             same_process = man["pid"] == _pid()
             for base, hx in man["handles"].items():
                 opened[base] = base if same_process else K.ipc_open_handle(bytes.fromhex(hx))
+            # In-place targets are matched by KEY PATH, not by position: a freshly restarted replica's
+            # state_dict usually has a different shape than the survivor's (e.g. a torch optimizer
+            # creates its per-parameter state lazily, so it is empty before the first step). Leaves
+            # without a matching target are simply allocated.
             dst_leaves: Optional[List[Any]] = None
             if self._inplace_state_dict is not None:
-                dst_leaves, dst_spec = pytree.tree_flatten(self._inplace_state_dict())
-                if len(dst_leaves) != len(man["items"]):
-                    raise RuntimeError("in-place state_dict does not match the received checkpoint structure")
+                targets = {pytree.keystr(kp): leaf
+                           for kp, leaf in pytree.tree_flatten_with_path(self._inplace_state_dict())[0]}
+                index_tree = pytree.tree_unflatten(list(range(len(man["items"]))), man["spec"])
+                dst_leaves = [None] * len(man["items"])
+                for kp, idx in pytree.tree_flatten_with_path(index_tree)[0]:
+                    dst_leaves[idx] = targets.get(pytree.keystr(kp))
             out: List[Any] = []
             entries: List[Tuple[int, int, int]] = []
             total = 0

@@ -128,11 +128,15 @@ class PGTransport(CheckpointTransport[T], Generic[T]):
         header: _Header = pickle.loads(bytes(hdr.cpu().numpy().tobytes()))
         if header.step != step:
             raise RuntimeError(f"checkpoint step mismatch: expected {step}, sender has {header.step}")
+        # in-place targets are matched by key path (a restarted replica's state_dict can be structurally
+        # smaller than the sender's, e.g. lazily created optimizer state); unmatched leaves are allocated
         inplace: Optional[List[Any]] = None
         if self._state_dict is not None:
-            inplace, _ = pytree.tree_flatten(self._state_dict())
-            if len(inplace) != len(header.leaves):
-                raise RuntimeError("in-place state_dict does not match the received checkpoint structure")
+            targets = {pytree.keystr(kp): leaf for kp, leaf in pytree.tree_flatten_with_path(self._state_dict())[0]}
+            index_tree = pytree.tree_unflatten(list(range(len(header.leaves))), header.treespec)
+            inplace = [None] * len(header.leaves)
+            for kp, idx in pytree.tree_flatten_with_path(index_tree)[0]:
+                inplace[idx] = targets.get(pytree.keystr(kp))
         out: List[Any] = []
         ti = 0
         for i, rec in enumerate(header.leaves):
