@@ -29,6 +29,10 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--mtbf-secs", type=float, default=10.0)
     ap.add_argument("--failures", default="kill_proc,segfault,comms,kill_group")
+    ap.add_argument("--min-replicas", type=int, default=1,
+                    help="1: survivors keep training alone while a victim restarts (needs enough steps after the last failure for it "
+                         "to rejoin); = --replicas: survivors stall until the victim is back (deterministic end state)")
+    ap.add_argument("--max-failures", type=int, default=0)
     ap.add_argument("--inject-until", type=float, default=0.5, help="fraction of --steps after which no more failures are injected")
     ap.add_argument("--timeout", type=int, default=420)
     ap.add_argument("--out", default="gpurun_out/chaos_soak.json")
@@ -36,7 +40,7 @@ def main() -> None:
     work = tempfile.mkdtemp(prefix="tft_soak_")
     env = dict(os.environ, TRAIN_STEPS=str(a.steps), TRAIN_OUT=os.path.join(work, "final_{group}.pt"), LOGLEVEL="INFO")
     cmd = [sys.executable, os.path.join(ROOT, "examples/orchestrator/train_orchestrated.py"), "--replicas", str(a.replicas),
-           "--gpus-per-node", str(max(torch.cuda.device_count(), 1)), "--min-replicas", "1", "--join-timeout-ms", "2000",
+           "--gpus-per-node", str(max(torch.cuda.device_count(), 1)), "--min-replicas", str(a.min_replicas), "--inject-below-min", "--max-failures", str(a.max_failures), "--join-timeout-ms", "2000",
            "--mtbf-secs", str(a.mtbf_secs), "--failures", a.failures, "--relaunch-delay", "1", "--log-dir", work,
            "--stop-injecting-at-step", str(int(a.steps * a.inject_until)),
            os.path.join(ROOT, "train_ddp.py")]

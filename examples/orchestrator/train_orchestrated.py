@@ -115,6 +115,9 @@ def main() -> None:
     ap.add_argument("--mtbf-secs", type=float, default=0.0, help="mean time between injected failures (0 = none)")
     ap.add_argument("--failures", default="kill_proc,segfault,comms,kill_group",
                     help="comma list from: " + ",".join([f.value for f in Failure] + [OUTSIDE_KILL]))
+    ap.add_argument("--max-failures", type=int, default=0, help="stop injecting after this many failures (0 = unlimited)")
+    ap.add_argument("--inject-below-min", action="store_true",
+                    help="also inject when that takes the job below --min-replicas (survivors then stall until the victim is back)")
     ap.add_argument("--stop-injecting-at-step", type=int, default=0,
                     help="no more failures once any group logged `step=N` with N >= this (0 = never stop); lets a soak "
                          "end with all groups in one quorum so their final weights can be compared")
@@ -166,13 +169,16 @@ def main() -> None:
                 break
             if now >= next_failure:
                 next_failure = now + rng.expovariate(1.0 / a.mtbf_secs)
+                if a.max_failures and sum(stats.values()) >= a.max_failures:
+                    next_failure = float("inf")
+                    continue
                 if a.stop_injecting_at_step and max(g.logged_step() for g in groups) >= a.stop_injecting_at_step:
                     next_failure = float("inf")
                     print(f"[{now - t0:7.1f}s] step {a.stop_injecting_at_step} reached: no more failures", flush=True)
                     continue
                 victims = [g for g in groups if g.alive() and g.role.name not in done]
-                if len(victims) <= a.min_replicas:  # never take the job below its quorum floor
-                    continue
+                if not victims or (len(victims) <= a.min_replicas and not a.inject_below_min):
+                    continue  # by default never take the job below its quorum floor
                 g, kind = rng.choice(victims), rng.choice(kinds)
                 stats[kind] = stats.get(kind, 0) + 1
                 print(f"[{now - t0:7.1f}s] injecting {kind} into {g.role.name}", flush=True)

@@ -62,9 +62,10 @@ class EventInjector:
             self._events[(rank, step)] = Event(EventType.FAILURE)
         return self
 
-    def fail_allreduce_at(self, rank: int, step: int) -> "EventInjector":
+    def fail_allreduce_at(self, rank: int, step: int, times: int = 1) -> "EventInjector":
+        """``times`` > 1: that many replica threads reaching (rank, step) each get the failure."""
         with self._lock:
-            self._events[(rank, step)] = Event(EventType.ALLREDUCE_FAILURE)
+            self._events[(rank, step)] = Event(EventType.ALLREDUCE_FAILURE, times)
         return self
 
     def barrier_at(self, rank: int, step: int, barrier: threading.Barrier) -> "EventInjector":
@@ -74,9 +75,13 @@ class EventInjector:
 
     def check(self, rank: int, step: int, pg: Optional[FakeProcessGroupWrapper] = None) -> None:
         with self._lock:
-            ev = self._events.pop((rank, step), None)
+            ev = self._events.get((rank, step))
             if ev is None:
                 return
+            if ev.kind == EventType.ALLREDUCE_FAILURE and isinstance(ev.data, int) and ev.data > 1:
+                ev.data -= 1  # more replicas still have to see this one
+            else:
+                del self._events[(rank, step)]
             self.count[ev.kind] += 1
         if ev.kind == EventType.FAILURE:
             raise InjectedFailure(f"injected failure {rank=} {step=}")
@@ -113,8 +118,12 @@ class Runner:
     transport: str = "http"
     same_init: bool = False
     manager_kwargs: Dict[str, Any] = field(default_factory=dict)
+    start_after: Optional[threading.Event] = None          # late joiner: wait for this before starting
+    signal_at: Optional[Tuple[int, threading.Event]] = None  # (step, event): set the event once that step is reached
 
     def run(self) -> List[Dict[str, Any]]:
+        if self.start_after is not None:
+            assert self.start_after.wait(60), "late joiner was never released"
         for attempt in range(self.attempts):
             try:
                 return self._run_group()
@@ -177,6 +186,8 @@ class Runner:
                 loss.backward()
                 self.injector.check(rank, manager.current_step(), pg)
                 opt.step()
+                if self.signal_at is not None and manager.current_step() >= self.signal_at[0]:
+                    self.signal_at[1].set()
             return {"state": {k: v.clone() for k, v in m.state_dict().items()}, "step": manager.current_step(),
                     "batches": manager.batches_committed()}
 
@@ -234,6 +245,33 @@ def test_ddp_allreduce_failure_is_discarded(lighthouse):
     res = _run([Runner(i, lighthouse.address(), inj, total_steps=4) for i in range(2)])
     assert inj.count[EventType.ALLREDUCE_FAILURE] == 1
     _assert_equal_state(res)
+
+
+def test_ddp_commit_failure_on_every_replica(lighthouse):
+    """The same step fails on BOTH replicas (reference: local_sgd_integ_test 'commit failure'): nobody commits it,
+    nobody diverges, the quorum id is bumped and training resumes."""
+    inj = EventInjector().fail_allreduce_at(0, 1, times=2)
+    res = _run([Runner(i, lighthouse.address(), inj, total_steps=4) for i in range(2)])
+    assert inj.count[EventType.ALLREDUCE_FAILURE] == 2
+    _assert_equal_state(res)
+    assert all(r[0]["step"] == 4 for r in res)
+    # the failed step consumed a batch on each replica without being committed
+    assert res[0][0]["batches"] == 8
+
+
+def test_ddp_upscale_third_replica_joins_late(lighthouse):
+    """Two replicas train; a third starts once they reached step 2 (reference: 'upscale'). It must be admitted,
+    heal live from an up-to-date peer, and all three must finish with identical weights."""
+    inj = EventInjector()
+    go = threading.Event()
+    runners = [Runner(0, lighthouse.address(), inj, total_steps=8, signal_at=(2, go)),
+               Runner(1, lighthouse.address(), inj, total_steps=8),
+               Runner(2, lighthouse.address(), inj, total_steps=8, start_after=go)]
+    res = _run(runners)
+    _assert_equal_state(res)
+    assert all(r[0]["step"] == 8 for r in res)
+    # the late joiner did not replay the steps it missed: it committed fewer batches than the founders' total
+    assert res[2][0]["batches"] == res[0][0]["batches"]  # batches_committed is global state carried by the heal
 
 
 def test_multi_rank_replica_groups(lighthouse):
