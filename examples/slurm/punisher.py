@@ -13,17 +13,25 @@ version computes such a draw and then sleeps the fixed MTBF, punisher.py:49-51).
 from __future__ import annotations
 
 import argparse
+import json
 import random
 import re
 import time
+import urllib.error
 import urllib.parse
 import urllib.request
 from typing import List
 
 
 def replicas(lighthouse: str) -> List[str]:
-    html = urllib.request.urlopen(lighthouse.rstrip("/") + "/status", timeout=10).read().decode()
-    return re.findall(r"kill\('([^']+)'\)", html)
+    """Replica ids of the current quorum (GET /status.json; falls back to scraping the HTML dashboard)."""
+    base = lighthouse.rstrip("/")
+    try:
+        st = json.loads(urllib.request.urlopen(base + "/status.json", timeout=10).read().decode())
+        return [p["replica_id"] for p in (st.get("prev_quorum") or {}).get("participants", [])]
+    except (urllib.error.HTTPError, ValueError):
+        html = urllib.request.urlopen(base + "/status", timeout=10).read().decode()
+        return re.findall(r"kill\('([^']+)'\)", html)
 
 
 def kill(lighthouse: str, replica_id: str) -> None:

@@ -411,6 +411,22 @@ def test_dashboard_http(lighthouse):
         urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{port}/replica/nobody/kill", method="POST"))
 
 
+def test_status_json(lighthouse):
+    import json
+
+    c = _C.LighthouseClient(lighthouse.address(), timedelta(seconds=5))
+    c.quorum('we"ird\\id', timedelta(seconds=5), address="http://nowhere:1", store_address="s:1", step=9, world_size=2)
+    port = lighthouse.address().rsplit(":", 1)[1]
+    r = urllib.request.urlopen(f"http://127.0.0.1:{port}/status.json")
+    assert r.headers["Content-Type"].startswith("application/json")
+    st = json.loads(r.read().decode())
+    assert st["quorum_id"] >= 1 and st["prev_quorum"]["max_step"] == 9
+    (p,) = st["prev_quorum"]["participants"]
+    assert p["replica_id"] == 'we"ird\\id' and p["step"] == 9 and p["world_size"] == 2 and p["recovering"] is False
+    assert st["heartbeats"]['we"ird\\id']["alive"] is True
+    assert isinstance(st["next_quorum_status"], str) and st["min_replicas"] == 1
+
+
 def test_native_selftest_binary():
     """The C++ control plane's own unit + integration tests (the reference runs `cargo test`)."""
     import subprocess

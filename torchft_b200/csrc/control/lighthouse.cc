@@ -205,6 +205,73 @@ std::string Lighthouse::status_html() {
   return os.str();
 }
 
+static std::string json_escape(const std::string& s) {
+  std::string o;
+  o.reserve(s.size() + 2);
+  for (unsigned char c : s) {
+    switch (c) {
+      case '"': o += "\\\""; break;
+      case '\\': o += "\\\\"; break;
+      case '\n': o += "\\n"; break;
+      case '\r': o += "\\r"; break;
+      case '\t': o += "\\t"; break;
+      default:
+        if (c < 0x20) {
+          char buf[8];
+          std::snprintf(buf, sizeof(buf), "\\u%04x", c);
+          o += buf;
+        } else {
+          o += (char)c;
+        }
+    }
+  }
+  return o;
+}
+
+// Machine-readable twin of the dashboard (GET /status.json): what monitoring and chaos tools poll.
+std::string Lighthouse::status_json() {
+  std::lock_guard<std::mutex> g(mu_);
+  const int64_t now = monotonic_ms();
+  QuorumDecision d = quorum_compute(now, state_, opt_);
+  std::ostringstream os;
+  os << "{\"quorum_id\": " << state_.quorum_id << ", \"next_quorum_status\": \"" << json_escape(d.reason)
+     << "\", \"next_quorum_ready\": " << (d.participants.has_value() ? "true" : "false")
+     << ", \"min_replicas\": " << opt_.min_replicas << ", \"heartbeat_timeout_ms\": " << opt_.heartbeat_timeout_ms
+     << ", \"prev_quorum\": ";
+  if (state_.prev_quorum) {
+    int64_t max_step = -1;
+    for (const auto& p : state_.prev_quorum->participants) max_step = std::max(max_step, p.step);
+    os << "{\"quorum_id\": " << state_.prev_quorum->quorum_id << ", \"age_s\": "
+       << (unix_ms() - state_.prev_quorum->created_ms) / 1000.0 << ", \"max_step\": " << max_step << ", \"participants\": [";
+    bool first = true;
+    for (const auto& p : state_.prev_quorum->participants) {
+      os << (first ? "" : ", ") << "{\"replica_id\": \"" << json_escape(p.replica_id) << "\", \"address\": \""
+         << json_escape(p.address) << "\", \"store_address\": \"" << json_escape(p.store_address) << "\", \"step\": " << p.step
+         << ", \"world_size\": " << p.world_size << ", \"recovering\": " << (p.step != max_step ? "true" : "false")
+         << ", \"commit_failures\": " << p.commit_failures << "}";
+      first = false;
+    }
+    os << "]}";
+  } else {
+    os << "null";
+  }
+  os << ", \"waiting\": [";
+  bool first = true;
+  for (const auto& [id, det] : state_.participants) {
+    os << (first ? "" : ", ") << "\"" << json_escape(id) << "\"";
+    first = false;
+  }
+  os << "], \"heartbeats\": {";
+  first = true;
+  for (const auto& [id, last] : state_.heartbeats) {
+    os << (first ? "" : ", ") << "\"" << json_escape(id) << "\": {\"age_s\": " << (now - last) / 1000.0 << ", \"alive\": "
+       << ((now - last) < (int64_t)opt_.heartbeat_timeout_ms ? "true" : "false") << "}";
+    first = false;
+  }
+  os << "}}";
+  return os.str();
+}
+
 HttpResponse Lighthouse::kill_replica(const std::string& replica_id) {
   std::string addr;
   {
@@ -239,6 +306,7 @@ static std::string url_decode(const std::string& s) {
 HttpResponse Lighthouse::handle_http(const HttpRequest& req) {
   if (req.method == "GET" && (req.path == "/" || req.path == "/index.html")) return {200, "text/html; charset=utf-8", kIndexHtml};
   if (req.method == "GET" && req.path == "/status") return {200, "text/html; charset=utf-8", status_html()};
+  if (req.method == "GET" && req.path == "/status.json") return {200, "application/json", status_json()};
   const std::string pre = "/replica/", suf = "/kill";
   if (req.method == "POST" && req.path.rfind(pre, 0) == 0 && req.path.size() > pre.size() + suf.size() &&
       req.path.compare(req.path.size() - suf.size(), suf.size(), suf) == 0) {

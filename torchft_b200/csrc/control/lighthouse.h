@@ -27,6 +27,7 @@ class Lighthouse : public RpcServer {
   void tick_locked();  // requires mu_
   void tick_loop();
   std::string status_html();
+  std::string status_json();
   HttpResponse kill_replica(const std::string& replica_id);
 
   LighthouseOpt opt_;
