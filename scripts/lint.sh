@@ -8,3 +8,4 @@ for f in torchft_b200/csrc/kernels/*.cu; do
   nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ \
        $(python -m pybind11 --includes) -I torchft_b200/csrc/kernels -c "$f" -o /dev/null
 done
+python scripts/lint_unused.py

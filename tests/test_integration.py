@@ -10,19 +10,19 @@ with IDENTICAL state_dicts. Replica groups are threads; ranks within a group are
 import logging
 import threading
 import time
-from concurrent.futures import ThreadPoolExecutor, as_completed
+from concurrent.futures import ThreadPoolExecutor
 from contextlib import ExitStack
 from dataclasses import dataclass, field
 from datetime import timedelta
 from enum import Enum, auto
-from typing import Any, Dict, List, Optional, Set, Tuple
+from typing import Any, Dict, List, Optional, Tuple
 
 import pytest
 import torch
 from torch import nn, optim
 from torch.distributed import TCPStore
 
-from torchft_b200.checkpointing import HTTPTransport, PGTransport
+from torchft_b200.checkpointing import PGTransport
 from torchft_b200.coordination import LighthouseServer
 from torchft_b200.ddp import DistributedDataParallel
 from torchft_b200.manager import Manager

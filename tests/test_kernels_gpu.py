@@ -1,6 +1,5 @@
 """Numerics of the hand-written sm_100a kernels vs plain PyTorch fp32 references."""
 
-import math
 
 import pytest
 import torch

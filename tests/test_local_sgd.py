@@ -4,7 +4,6 @@ Gloo replicas (healthy, recovery, commit failure). Mirrors the reference's local
 local_sgd_integ_test.py scenarios; the oracle for integration is identical global state."""
 
 import copy
-import threading
 from concurrent.futures import ThreadPoolExecutor
 from datetime import timedelta
 from typing import Any, Dict, List
@@ -16,7 +15,7 @@ from torch import nn, optim
 from torch.distributed import TCPStore
 
 from torchft_b200.coordination import LighthouseServer
-from torchft_b200.local_sgd import DiLoCo, LocalSGD, extract_local_tensor
+from torchft_b200.local_sgd import DiLoCo, LocalSGD
 from torchft_b200.manager import Manager
 from torchft_b200.process_group import FakeProcessGroupWrapper, ProcessGroupGloo
 from torchft_b200.work import DummyWork

@@ -6,7 +6,6 @@ FIXED_WITH_SPARES, allow_heal=False, wrap_future timeouts, numerics per op,
 timeouts plumbed, max_retries, state-dict locking).
 """
 
-import threading
 import time
 from datetime import timedelta
 from typing import Optional

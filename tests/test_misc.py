@@ -12,13 +12,12 @@ from unittest.mock import MagicMock, create_autospec, patch
 import pytest
 import torch
 from torch import nn
-from torch.distributed import ReduceOp
 from torch.futures import Future
 
 from torchft_b200 import coordination
 from torchft_b200.data import DistributedSampler
 from torchft_b200.ddp import DistributedDataParallel, PureDistributedDataParallel
-from torchft_b200.futures import _TIMEOUT_MANAGER, context_timeout, future_timeout, future_wait
+from torchft_b200.futures import context_timeout, future_timeout, future_wait
 from torchft_b200.manager import Manager
 from torchft_b200.multiprocessing import _MonitoredPipe
 from torchft_b200.optim import OptimizerWrapper

@@ -24,16 +24,7 @@ from torch.distributed.distributed_c10d import (
 
 from torchft_b200.baby import ProcessGroupBabyGloo
 from torchft_b200.manager import Manager
-from torchft_b200.process_group import (
-    ErrorSwallowingProcessGroupWrapper,
-    FakeProcessGroupWrapper,
-    ManagedProcessGroup,
-    ProcessGroup,
-    ProcessGroupDummy,
-    ProcessGroupGloo,
-    ProcessGroupWrapper,
-    create_store_client,
-)
+from torchft_b200.process_group import ErrorSwallowingProcessGroupWrapper, FakeProcessGroupWrapper, ManagedProcessGroup, ProcessGroup, ProcessGroupDummy, ProcessGroupGloo, create_store_client
 
 
 def _store():

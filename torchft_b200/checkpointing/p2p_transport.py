@@ -24,7 +24,6 @@ Roofline: bytes / 770 GB/s (one NVLink direction); the source's SMs are not used
 from __future__ import annotations
 
 import io
-import json
 import logging
 import pickle
 import socket

@@ -11,15 +11,14 @@
 """
 
 import os
-from typing import TYPE_CHECKING, Any, Callable, Dict, List, Optional, Tuple
+from typing import TYPE_CHECKING, Any, Dict, List, Tuple
 
 import torch
 import torch.distributed as dist
 from torch import nn
-from torch.distributed.algorithms.join import Joinable
 from torch.nn import parallel
 
-from torchft_b200.process_group import ProcessGroup, ProcessGroupDummy
+from torchft_b200.process_group import ProcessGroupDummy
 
 if TYPE_CHECKING:
     from torchft_b200.manager import Manager

@@ -19,8 +19,8 @@ implementation, laid out for one-GPU-per-replica training in 180 GB of HBM3e:
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, asdict
-from typing import Callable, Dict, Iterator, List, Optional, Tuple
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn

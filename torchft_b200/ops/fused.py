@@ -7,8 +7,7 @@ There is no PyTorch fallback: on a CUDA box these always run ``_K`` kernels.
 
 from __future__ import annotations
 
-import math
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 

@@ -28,8 +28,7 @@ from datetime import timedelta
 from typing import Any, List, Optional
 
 import torch
-import torch.distributed as dist
-from torch.distributed import PrefixStore, ReduceOp, Store, Work
+from torch.distributed import PrefixStore, ReduceOp, Work
 from torch.futures import Future
 
 from torchft_b200.ops import _native

@@ -30,25 +30,15 @@ from __future__ import annotations
 
 import logging
 import os
-import threading
-import warnings
-from contextlib import contextmanager, nullcontext
+from contextlib import contextmanager
 from datetime import timedelta
-from typing import TYPE_CHECKING, Any, Callable, Dict, Generator, List, Optional, Tuple, TypeVar, Union
+from typing import TYPE_CHECKING, Any, Callable, Dict, Generator, List, Optional, Tuple, TypeVar
 
 import torch
 import torch.distributed as dist
 from torch.distributed import PrefixStore, ReduceOp, Store, TCPStore, Work
 from torch.distributed import ProcessGroup as BaseProcessGroup
-from torch.distributed.distributed_c10d import (
-    AllgatherOptions,
-    AllreduceCoalescedOptions,
-    AllreduceOptions,
-    AllToAllOptions,
-    BarrierOptions,
-    BroadcastOptions,
-    ReduceScatterOptions,
-)
+from torch.distributed.distributed_c10d import AllgatherOptions, BarrierOptions, BroadcastOptions
 from torch.futures import Future
 
 from torchft_b200.futures import context_timeout, stream_timeout

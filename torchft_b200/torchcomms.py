@@ -25,7 +25,7 @@ from __future__ import annotations
 
 import logging
 from datetime import timedelta
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Any, List, Optional, Tuple
 
 import torch
 from torch.distributed.distributed_c10d import ReduceOp, Work
