@@ -173,8 +173,9 @@ class FlatParams:
     ``grad_alloc(numel) -> Tensor`` lets the caller place the gradient buffer in
     NVLink-symmetric memory (``ProcessGroupB200.alloc_symmetric``); buckets for
     the overlapped cross-replica all-reduce are contiguous slices of it.
-    Parameters are laid out in REVERSE registration order so that buckets fill
-    front-to-back in the order backward produces gradients.
+    Parameters are laid out in reverse FORWARD order (``module.param_stages()`` when the module
+    provides it, else reverse registration order) so that buckets fill front-to-back in the
+    order backward produces gradients.
     """
 
     ALIGN = 128  # elements; keeps every view 256 B aligned
@@ -190,7 +191,18 @@ class FlatParams:
             # buffer (no transient second copy of the weights); caller initialises after.
             assert device is not None, "pass device= when flattening a meta module"
             dev = torch.device(device)
-        order = list(reversed(named))
+        # Gradient-production order = reverse of first use in forward. Registration order is only a proxy
+        # (a module's own parameters are listed before its children's), so a model that knows its forward
+        # order says so through ``param_stages()``: for Llama that puts the LM head and final norm FIRST
+        # (their gradients exist at the very start of backward and their all-reduce then hides under the
+        # rest of it) and the embedding last.
+        if hasattr(module, "param_stages"):
+            name_of = {id(p): n for n, p in named}
+            fwd = [p for stage in module.param_stages() for p in stage if id(p) in name_of]
+            assert len({id(p) for p in fwd}) == len(named), "param_stages() must cover every parameter exactly once"
+            order = [(name_of[id(p)], p) for p in reversed(fwd)]
+        else:
+            order = list(reversed(named))
         offs, total = [], 0
         for _, p in order:
             offs.append(total)
