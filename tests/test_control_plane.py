@@ -437,3 +437,53 @@ def test_native_selftest_binary():
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failed" in r.stdout
+
+
+def test_server_survives_malformed_traffic(lighthouse):
+    """Garbage, truncated frames, absurd lengths, unknown methods and undecodable payloads must never take the
+    Lighthouse down or wedge it (the reference gets this from tonic/hyper; our framing is hand-written)."""
+    import os
+    import socket
+    import struct
+
+    port = int(lighthouse.address().rsplit(":", 1)[1])
+
+    def raw(data: bytes, read: bool = True, linger: float = 0.2) -> bytes:
+        s = socket.create_connection(("127.0.0.1", port), timeout=5)
+        try:
+            s.sendall(data)
+            if not read:
+                return b""
+            s.settimeout(linger)
+            try:
+                return s.recv(65536)
+            except (socket.timeout, ConnectionResetError):
+                return b""
+        finally:
+            s.close()
+
+    def frame(method: int, payload: bytes, timeout_ms: int = 1000, length: int = -1) -> bytes:
+        return b"TFT1" + struct.pack("<IQI", method, timeout_ms, len(payload) if length < 0 else length) + payload
+
+    rng_bytes = os.urandom(4096)
+    raw(rng_bytes)                                     # not our magic, not HTTP
+    raw(b"GET /nope HTTP/1.1\r\n\r\n")                 # unknown HTTP path -> 404
+    raw(b"GET " + b"A" * 100000)                       # endless request line, never terminated
+    raw(b"TFT", read=False)                            # truncated magic, then EOF
+    raw(b"TFT1" + b"\x01\x00", read=False)             # truncated header
+    raw(frame(1, b"\x00" * 10, length=1 << 31), read=False)      # claims 2 GiB: must be refused, not allocated
+    raw(frame(1, b"\x00" * 10, length=5000), read=False)         # claims more than it sends, then EOF
+    for method in (0, 7, 999, 2 ** 32 - 1):            # unknown methods -> error status, connection stays sane
+        resp = raw(frame(method, b"hello"))
+        assert len(resp) >= 8 and struct.unpack("<I", resp[:4])[0] != 0
+    for method in (1, 2):                              # known methods, undecodable payloads
+        for payload in (b"", b"\xff" * 3, rng_bytes[:64], struct.pack("<I", 2 ** 31) + b"x"):
+            resp = raw(frame(method, payload))
+            assert len(resp) >= 8 and struct.unpack("<I", resp[:4])[0] != 0, (method, payload[:8])
+    # ... and it still does its job
+    c = _C.LighthouseClient(lighthouse.address(), timedelta(seconds=5))
+    q = c.quorum("after_fuzz", timedelta(seconds=5), address="http://x:1", step=1)
+    assert [p.replica_id for p in q.participants] == ["after_fuzz"]
+    c.heartbeat("after_fuzz", timedelta(seconds=1))
+    status = urllib.request.urlopen(f"http://127.0.0.1:{port}/status.json").read()
+    assert b"after_fuzz" in status
