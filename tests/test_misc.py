@@ -106,6 +106,35 @@ def test_optimizer_wrapper_gates_step_on_commit():
 
 
 # -------------------------------------------------------------------------- ddp
+def test_optimizer_wrapper_works_with_lr_schedulers_and_forwards_state():
+    from unittest.mock import MagicMock
+
+    from torchft_b200.optim import OptimizerWrapper
+
+    manager = MagicMock()
+    manager.should_commit.return_value = True
+    p = torch.nn.Parameter(torch.ones(3))
+    inner = torch.optim.SGD([p], lr=0.1, momentum=0.9)
+    opt = OptimizerWrapper(manager, inner)
+    assert isinstance(opt, torch.optim.Optimizer)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)  # patches opt.step on the facade only
+    p.grad = torch.ones(3)
+    opt.step()
+    sched.step()
+    assert opt.last_step_committed and torch.allclose(p.data, torch.full((3,), 0.9))
+    assert opt.param_groups is inner.param_groups and inner.param_groups[0]["lr"] == pytest.approx(0.05)
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == 1  # momentum buffer of the inner optimizer
+    opt.load_state_dict(sd)
+    manager.should_commit.return_value = False
+    p.grad = torch.ones(3)
+    before = p.data.clone()
+    opt.step()
+    assert not opt.last_step_committed and torch.equal(p.data, before)
+    with pytest.raises(NotImplementedError):
+        opt.step(closure=lambda: 0.0)
+
+
 def test_ddp_wrapper_routes_buckets_through_manager():
     manager = create_autospec(Manager)
     manager.allreduce.side_effect = lambda t, **kw: DummyWork(t)
@@ -181,7 +210,7 @@ def test_otel_requested_but_missing_raises(monkeypatch):
 def test_coordination_api_is_documented():
     for name in coordination.__all__:
         obj = getattr(coordination, name)
-        assert obj is not None
+        assert obj is not None and (obj.__doc__ or "").strip(), f"{name} is undocumented"
     assert "quorum" in (coordination.__doc__ or "").lower()
     q = coordination.QuorumResult()
     assert q.quorum_id == 0 and q.recover_src_replica_rank is None and q.replica_ids == []
@@ -198,6 +227,24 @@ def test_monitored_pipe_timeout_and_exception_transport():
     pb.send(ValueError("remote"))
     with pytest.raises(ValueError, match="remote"):
         pa.recv(1.0)
+    # failures sent as an envelope keep the remote traceback as __cause__
+    from torchft_b200.multiprocessing import failure_of
+
+    try:
+        raise KeyError("deep in the child")
+    except KeyError as e:
+        pb.send(failure_of(e))
+    with pytest.raises(KeyError) as ei:
+        pa.recv(1.0)
+    assert "deep in the child" in str(ei.value.__cause__) and "Traceback" in str(ei.value.__cause__)
+    # a dead peer is noticed long before the deadline
+    import time
+
+    watched = _MonitoredPipe(a, alive=lambda: False)
+    t0 = time.monotonic()
+    with pytest.raises(RuntimeError, match="exited"):
+        watched.recv(30.0)
+    assert time.monotonic() - t0 < 2.0
 
 
 def test_get_padded_sizes_and_reduce_scatter_output():

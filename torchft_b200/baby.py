@@ -38,7 +38,7 @@ from torch.distributed.distributed_c10d import (
 )
 from torch.futures import Future
 
-from torchft_b200.multiprocessing import _MonitoredPipe
+from torchft_b200.multiprocessing import MonitoredPipe, failure_of
 from torchft_b200.process_group import _FORWARDED, ProcessGroup, ProcessGroupGloo, ProcessGroupNCCL
 
 logger = logging.getLogger(__name__)
@@ -131,7 +131,7 @@ def _child_main(pg_factory: Callable[[timedelta], ProcessGroup], store_addr: str
         pg.configure(store_addr, *cfg)
         resp.send(("ready",))
     except Exception as e:  # noqa: BLE001
-        resp.send(e)
+        resp.send(failure_of(e))
         return
     works: Dict[int, Work] = {}
     while True:
@@ -165,7 +165,7 @@ def _child_main(pg_factory: Callable[[timedelta], ProcessGroup], store_addr: str
                 raise ValueError(f"unknown command {op}")
         except Exception as e:  # noqa: BLE001
             try:
-                resp.send(e)
+                resp.send(failure_of(e))
             except Exception:  # noqa: BLE001
                 return
 
@@ -208,7 +208,7 @@ class ProcessGroupBaby(ProcessGroup):
         self._rank = -1
         self._proc: Optional[Any] = None
         self._req: Optional[Any] = None
-        self._resp: Optional[_MonitoredPipe] = None
+        self._resp: Optional[MonitoredPipe] = None
         self._lock = threading.RLock()
         self._next_op = 0
         self._error: Optional[Exception] = None
@@ -240,7 +240,7 @@ class ProcessGroupBaby(ProcessGroup):
             daemon=True,
         )
         self._proc.start()
-        self._req, self._resp = req_parent, _MonitoredPipe(resp_parent)
+        self._req, self._resp = req_parent, MonitoredPipe(resp_parent, alive=getattr(self._proc, "is_alive", None))
         # the child's PG creation is a rendezvous with its peers: allow the full timeout (+ process start)
         msg = self._resp.recv(self._timeout + timedelta(seconds=30))
         assert msg == ("ready",), msg

@@ -1,57 +1,91 @@
-"""Optimizer wrapper that drives the fault-tolerance protocol
-(reference: /root/reference/torchft/optim.py:24-63).
+"""Optimizer facade that drives the per-step fault-tolerance protocol.
 
-``zero_grad()`` starts the step's quorum, ``step()`` only applies the update when
-the replica group agrees the step is clean (``Manager.should_commit``).
+Behavioural parity with the reference's ``torchft/optim.py:24-63``: ``zero_grad()`` opens the
+step (starts the quorum, which overlaps the forward pass when the manager uses an async quorum)
+and ``step()`` applies the update only if every rank of the replica group — and therefore every
+participating replica — voted the step clean (``Manager.should_commit``).
+
+Implementation notes (ours): the facade owns no optimizer state. Everything that is not part of
+the protocol is *forwarded* to the wrapped object — by a generated method for names that
+``torch.optim.Optimizer`` defines itself, by ``__getattr__`` for the rest — so it works for any
+``torch.optim`` optimizer and for duck-typed ones such as :class:`torchft_b200.ops.fused.FlatAdamW`,
+and LR schedulers (which require an ``Optimizer`` instance and read ``param_groups``) keep working.
 """
 
 from __future__ import annotations
 
-from typing import TYPE_CHECKING, Any, Dict, List, Mapping, Optional
+from typing import TYPE_CHECKING, Any, Callable, Optional
 
-import torch
 from torch.optim import Optimizer
 
 if TYPE_CHECKING:
     from torchft_b200.manager import Manager
 
+__all__ = ["OptimizerWrapper"]
+
+_DATA = ("param_groups", "state", "defaults")
+
+# Optimizer methods that must reach the wrapped optimizer instead of the (uninitialised) base class
+_FORWARDED = ("add_param_group", "load_state_dict", "state_dict", "register_step_pre_hook", "register_step_post_hook",
+              "register_state_dict_pre_hook", "register_state_dict_post_hook", "register_load_state_dict_pre_hook",
+              "register_load_state_dict_post_hook")
+
 
 class OptimizerWrapper(Optimizer):
-    """Wrap any optimizer (torch or :class:`~torchft_b200.ops.fused.FlatAdamW`).
+    """``OptimizerWrapper(manager, inner)``; exported as ``torchft_b200.Optimizer``.
 
-        optim = OptimizerWrapper(manager, torch.optim.AdamW(m.parameters()))
-        optim.zero_grad()        # -> manager.start_quorum()
-        loss.backward()
-        optim.step()             # -> if manager.should_commit(): inner.step()
+        optim = OptimizerWrapper(manager, torch.optim.AdamW(model.parameters()))
+        optim.zero_grad()        # manager.start_quorum()
+        loss.backward()          # gradients averaged over the live replicas
+        optim.step()             # inner.step() iff manager.should_commit()
+
+    ``last_step_committed`` tells the training loop whether the most recent ``step()`` was applied.
     """
 
     def __init__(self, manager: "Manager", optim: Any) -> None:
-        # deliberately no Optimizer.__init__: all state lives in the wrapped optimizer
-        self.optim = optim
-        self.manager = manager
+        # no Optimizer.__init__ on purpose: defaults / param_groups / state all belong to `optim`
+        self.__dict__["optim"] = optim
+        self.__dict__["manager"] = manager
+        self.__dict__["last_step_committed"] = False
 
-    def add_param_group(self, param_group: Dict[str, Any]) -> None:
-        self.optim.add_param_group(param_group)
-
-    def load_state_dict(self, state_dict: Mapping[str, Any]) -> None:
-        self.optim.load_state_dict(state_dict)
-
-    def state_dict(self) -> Dict[str, Any]:
-        return self.optim.state_dict()
-
-    def zero_grad(self, set_to_none: bool = True) -> None:
+    # -- the protocol --------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = True) -> None:  # type: ignore[override]
         self.manager.start_quorum()
         self.optim.zero_grad(set_to_none)
 
-    def step(self, closure: Optional[object] = None) -> None:
-        assert closure is None, "optimizers that use closures are not supported"
-        if self.manager.should_commit():
+    def step(self, closure: Optional[Callable[[], float]] = None) -> None:  # type: ignore[override]
+        if closure is not None:
+            raise NotImplementedError("closure-based optimizers re-evaluate the loss outside the commit protocol")
+        self.last_step_committed = bool(self.manager.should_commit())
+        if self.last_step_committed:
             self.optim.step()
 
-    @property
-    def param_groups(self) -> List[Dict[str, Any]]:  # type: ignore[override]
-        return self.optim.param_groups
+    # -- everything else belongs to the wrapped optimizer ------------------------
+    def __getattr__(self, name: str) -> Any:  # only called when normal lookup fails
+        return getattr(self.__dict__["optim"], name)
 
-    @property
-    def state(self) -> Mapping[torch.Tensor, Any]:  # type: ignore[override]
-        return self.optim.state
+    def __setattr__(self, name: str, value: Any) -> None:
+        # the optimizer's DATA lives in the wrapped object; anything else (e.g. the `step` patch an LR
+        # scheduler installs to count calls) stays on the facade, exactly as for a plain Optimizer
+        if name in _DATA:
+            setattr(self.__dict__["optim"], name, value)
+        else:
+            self.__dict__[name] = value
+
+    def __repr__(self) -> str:
+        return f"OptimizerWrapper({self.optim!r})"
+
+
+def _forward(name: str) -> Callable[..., Any]:
+    def method(self: OptimizerWrapper, *args: Any, **kwargs: Any) -> Any:
+        return getattr(self.optim, name)(*args, **kwargs)
+
+    method.__name__ = name
+    method.__doc__ = f"Forwarded to the wrapped optimizer's ``{name}``."
+    return method
+
+
+for _name in _FORWARDED:
+    if hasattr(Optimizer, _name):
+        setattr(OptimizerWrapper, _name, _forward(_name))
+del _name
