@@ -275,3 +275,42 @@ def test_p2p_transport_inplace_targets_matched_by_key_path(K):
     finally:
         src.shutdown()
         dst.shutdown()
+
+
+def _rms(x, g, eps):
+    return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * g
+
+
+@pytest.mark.parametrize("with_res", [False, True])
+def test_fused_block_ops_match_fp32_reference(with_res):
+    """norm_linear(_res) / linear(res=) / swiglu_linear(res=): forward and every gradient (input, residual stream,
+    norm weight, projection weights) against a plain fp32 PyTorch graph of the same sub-block."""
+    from torchft_b200.ops import fused
+
+    torch.manual_seed(21)
+    T, H, F, eps = 48, 256, 384, 1e-5
+    mk = lambda *s, sc=1.0: (torch.randn(*s, device="cuda") * sc).bfloat16().requires_grad_()  # noqa: E731
+    x, g = mk(T, H), mk(H, sc=0.2)
+    with torch.no_grad():
+        g.add_(1.0)
+    W13, W2, Wo = mk(2 * F, H, sc=0.05), mk(H, F, sc=0.05), mk(H, H, sc=0.05)
+    if with_res:
+        xs, gu = fused.norm_linear_res(x, g, W13, eps)
+        h = fused.swiglu_linear(gu, W2, res=xs)
+        out = fused.linear(h, Wo, res=h)
+    else:
+        gu = fused.norm_linear(x, g, W13, eps)
+        h = x + fused.swiglu_linear(gu, W2)
+        out = h + fused.linear(h, Wo)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+
+    xf, gf, W13f, W2f, Wof = (t.detach().float().requires_grad_() for t in (x, g, W13, W2, Wo))
+    guf = _rms(xf, gf, eps) @ W13f.t()
+    hf = xf + (torch.nn.functional.silu(guf[:, :F]) * guf[:, F:]) @ W2f.t()
+    outf = hf + hf @ Wof.t()
+    outf.backward(dout.float())
+    assert _rel(out, outf) < 2e-2
+    for name, a, b in (("dx", x.grad, xf.grad), ("dg", g.grad, gf.grad), ("dW13", W13.grad, W13f.grad),
+                       ("dW2", W2.grad, W2f.grad), ("dWo", Wo.grad, Wof.grad)):
+        assert a is not None and _rel(a, b) < 3e-2, (name, _rel(a, b))
