@@ -254,3 +254,16 @@ def test_get_padded_sizes_and_reduce_scatter_output():
     assert get_padded_sizes(ts, 4) == [torch.Size([8, 3]), torch.Size([4]), torch.Size([8, 2])]
     out, padded = allocate_reduce_scatter_output(ts, 4)
     assert out.numel() == 6 + 1 + 4 and padded[0] == torch.Size([8, 3])
+
+
+def test_reference_import_paths_resolve():
+    """Names the reference exposes from torchft.process_group / torchft import the same way here."""
+    import torchft_b200
+    from torchft_b200.process_group import (  # noqa: F401
+        ErrorSwallowingProcessGroupWrapper, FakeProcessGroupWrapper, ManagedProcessGroup, ProcessGroup, ProcessGroupBabyGloo,
+        ProcessGroupBabyNCCL, ProcessGroupDummy, ProcessGroupGloo, ProcessGroupNCCL, ProcessGroupWrapper)
+
+    for name in ("Manager", "Optimizer", "DistributedDataParallel", "DistributedSampler", "ProcessGroupGloo", "ProcessGroupNCCL",
+                 "ProcessGroupBabyGloo", "ProcessGroupBabyNCCL", "ManagedProcessGroup", "WorldSizeMode"):
+        assert hasattr(torchft_b200, name), name
+    assert ProcessGroupBabyGloo is torchft_b200.ProcessGroupBabyGloo

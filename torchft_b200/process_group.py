@@ -718,3 +718,20 @@ class ManagedProcessGroup(ProcessGroup):
     def getBackendName(self) -> str:
         pg = self._manager._pg
         return pg.getBackendName() if isinstance(pg, ProcessGroup) else "torchft-managed"
+
+
+# The subprocess-hosted groups live in torchft_b200.baby (which imports this module); the reference exposes
+# them from process_group.py, so resolve those names lazily here for import compatibility.
+_BABY_NAMES = ("ProcessGroupBaby", "ProcessGroupBabyGloo", "ProcessGroupBabyNCCL")
+
+
+def __getattr__(name: str) -> Any:
+    if name in _BABY_NAMES:
+        from torchft_b200 import baby
+
+        return getattr(baby, name)
+    if name == "ProcessGroupB200":
+        from torchft_b200.parallel.process_group_b200 import ProcessGroupB200
+
+        return ProcessGroupB200
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
