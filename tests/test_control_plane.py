@@ -6,6 +6,7 @@ our implementation through the pybind11 module: pure decision functions first,
 then real servers on loopback (port 0) driven by real clients.
 """
 
+import os
 import threading
 import time
 import urllib.request
@@ -409,6 +410,28 @@ def test_dashboard_http(lighthouse):
     assert "dash" in status and "Step: 4" in status and "Heartbeats" in status
     with pytest.raises(urllib.error.HTTPError):
         urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{port}/replica/nobody/kill", method="POST"))
+
+
+@pytest.mark.parametrize("sanitize,needle", [("thread", "ThreadSanitizer"), ("address", "Sanitizer")])
+def test_native_selftest_under_sanitizers(sanitize, needle):
+    """Race detection / memory checking of the C++ control plane: the same selftest under TSan and ASan+UBSan.
+    (TSan found a real bug in round 1: a worker thread notified a condition variable after the server that owned
+    it could already be destroyed.)"""
+    import subprocess
+
+    from torchft_b200 import _build
+
+    try:
+        exe = _build.build_selftest(sanitize=sanitize)
+    except Exception as e:  # noqa: BLE001 - toolchain without the sanitizer runtime
+        pytest.skip(f"cannot build with -fsanitize={sanitize}: {e}")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 second_deadlock_stack=1", ASAN_OPTIONS="detect_leaks=1",
+               UBSAN_OPTIONS="print_stacktrace=1")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=env)
+    out = r.stdout + r.stderr
+    assert "0 failed" in r.stdout, out[-3000:]
+    assert needle not in out and "runtime error" not in out, out[-4000:]
+    assert r.returncode == 0
 
 
 def test_status_json(lighthouse):

@@ -147,13 +147,21 @@ def build_lighthouse_binary(force: bool = False) -> Path:
     return out
 
 
-def build_selftest(force: bool = False) -> Path:
-    """Native unit/integration tests of the control plane (`cargo test` equivalent): bin/torchft_b200_selftest."""
+def build_selftest(force: bool = False, sanitize: str = "") -> Path:
+    """Native unit/integration tests of the control plane (`cargo test` equivalent): bin/torchft_b200_selftest.
+
+    ``sanitize="thread"`` / ``"address"`` builds the same tests under ThreadSanitizer / AddressSanitizer+UBSan
+    (bin/torchft_b200_selftest_tsan / _asan) — the race and memory checks of the control plane."""
     cdir = CSRC / "control"
-    out = ROOT.parent / "bin" / "torchft_b200_selftest"
+    suffix = {"": "", "thread": "_tsan", "address": "_asan"}[sanitize]
+    out = ROOT.parent / "bin" / f"torchft_b200_selftest{suffix}"
     srcs = [cdir / f"{n}.cc" for n in ("wire", "quorum", "rpc", "lighthouse", "manager_server")] + [cdir / "tests" / "selftest.cc"]
     flags = ["-O1", "-g", "-std=c++17", "-pthread"]
-    stamp_file = BUILD / "selftest_bin.stamp"
+    if sanitize == "thread":
+        flags += ["-fsanitize=thread"]
+    elif sanitize == "address":
+        flags += ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
+    stamp_file = BUILD / f"selftest_bin{suffix}.stamp"
     stamp = _stamp(srcs + sorted(cdir.glob("*.h")), flags)
     if not force and out.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
         return out

@@ -55,13 +55,16 @@ void RpcServer::accept_loop() {
         serve(fd);
       } catch (...) {
       }
+      close_fd(fd);
       {
+        // Last touch of `this`: stop() may return (and the server be destroyed) the moment it observes
+        // workers_ == 0, so the notify must happen INSIDE the critical section, never after it
+        // (found by ThreadSanitizer: cv_ destroyed under a late notify_all).
         std::lock_guard<std::mutex> g(mu_);
         conns_.erase(fd);
         --workers_;
+        cv_.notify_all();
       }
-      close_fd(fd);
-      cv_.notify_all();
     }).detach();
   }
 }

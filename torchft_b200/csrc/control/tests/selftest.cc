@@ -4,6 +4,11 @@
 //
 //   build:  python -m torchft_b200._build   (-> bin/torchft_b200_selftest)
 //   run:    bin/torchft_b200_selftest [filter]
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -286,6 +291,70 @@ static void test_manager_group_barrier_and_commit() {
   lh.shutdown();
 }
 
+// Raw-socket abuse of a live server; most valuable under ASAN/UBSAN (scripts/sanitize.sh).
+static int raw_connect(const std::string& http_addr) {
+  const auto colon = http_addr.rfind(':');
+  const int port = std::stoi(http_addr.substr(colon + 1));
+  int fd = ::socket(AF_INET, SOCK_STREAM, 0);
+  sockaddr_in sa{};
+  sa.sin_family = AF_INET;
+  sa.sin_port = htons((uint16_t)port);
+  sa.sin_addr.s_addr = htonl(INADDR_LOOPBACK);
+  if (::connect(fd, (sockaddr*)&sa, sizeof(sa)) != 0) {
+    ::close(fd);
+    return -1;
+  }
+  return fd;
+}
+
+static void test_server_survives_garbage() {
+  LighthouseOpt opt;
+  opt.bind = "127.0.0.1:0";
+  opt.min_replicas = 1;
+  opt.join_timeout_ms = 50;
+  opt.quorum_tick_ms = 10;
+  Lighthouse lh(opt);
+  uint64_t x = 0x9e3779b97f4a7c15ull;  // xorshift: deterministic "random" bytes
+  auto next = [&x] {
+    x ^= x << 13;
+    x ^= x >> 7;
+    x ^= x << 17;
+    return x;
+  };
+  for (int round = 0; round < 60; ++round) {
+    int fd = raw_connect(lh.address());
+    CHECK(fd >= 0);
+    if (fd < 0) return;
+    std::string msg;
+    const int kind = round % 5;
+    if (kind == 0) {  // pure noise
+      for (int i = 0; i < 200; ++i) msg.push_back((char)next());
+    } else {          // valid magic, then a header with hostile fields and a short/garbage payload
+      msg = "TFT1";
+      uint32_t method = kind == 1 ? 1u : (kind == 2 ? 2u : (uint32_t)next());
+      uint64_t timeout_ms = kind == 3 ? ~0ull : 50;
+      uint32_t len = kind == 4 ? 0x7fffffffu : (uint32_t)(next() % 64);
+      msg.append((const char*)&method, 4);
+      msg.append((const char*)&timeout_ms, 8);
+      msg.append((const char*)&len, 4);
+      const int n = (int)(next() % 48);
+      for (int i = 0; i < n; ++i) msg.push_back((char)next());
+    }
+    (void)!::send(fd, msg.data(), msg.size(), MSG_NOSIGNAL);
+    if (round % 2) ::shutdown(fd, SHUT_WR);
+    char buf[256];
+    timeval tv{0, 20000};
+    ::setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    (void)!::recv(fd, buf, sizeof(buf), 0);
+    ::close(fd);
+  }
+  // still fully functional
+  LighthouseClient c(lh.address(), Millis(5000));
+  Quorum q = c.quorum(member("after_garbage", 1), Millis(5000));
+  CHECK(q.participants.size() == 1 && q.participants[0].replica_id == "after_garbage");
+  lh.shutdown();
+}
+
 int main(int argc, char** argv) {
   const char* filter = argc > 1 ? argv[1] : "";
   struct T {
@@ -303,6 +372,7 @@ int main(int argc, char** argv) {
       {"compute_quorum_results", test_compute_quorum_results},
       {"lighthouse_end_to_end", test_lighthouse_end_to_end},
       {"manager_group_barrier_and_commit", test_manager_group_barrier_and_commit},
+      {"server_survives_garbage", test_server_survives_garbage},
   };
   int ran = 0;
   for (const auto& t : tests) {
