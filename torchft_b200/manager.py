@@ -578,7 +578,7 @@ class Manager:
         when this returns True. Raises ``RuntimeError`` after more than ``max_retries``
         consecutive failures.
         """
-        with torch.profiler.record_function("torchft::manager::should_commmit::recovery_stream::synchronize"):
+        with torch.profiler.record_function("torchft::manager::should_commit::recovery_stream::synchronize"):
             if self._recovery_event is not None:
                 self._recovery_event.synchronize()
                 self._recovery_event = None

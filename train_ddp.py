@@ -105,6 +105,18 @@ def main() -> None:
         injector = FailureInjector(manager).start()
     print(m, f"{sum(p.numel() for p in m.parameters())} params", flush=True)
 
+    # PROFILE_DIR=/some/dir: chrome traces with the torchft::manager::* spans (quorum, configure, allreduce,
+    # should_commit, checkpoint send/recv) next to the kernels -- the reference's examples do the same
+    prof = None
+    if os.environ.get("PROFILE_DIR"):
+        from torch.profiler import ProfilerActivity, profile, schedule, tensorboard_trace_handler
+
+        acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if use_cuda else [])
+        prof = profile(activities=acts, schedule=schedule(wait=5, warmup=2, active=10, repeat=2),
+                       on_trace_ready=tensorboard_trace_handler(os.path.join(os.environ["PROFILE_DIR"], f"group{replica_group}")),
+                       record_shapes=True)
+        prof.start()
+
     epoch = 0
     while manager.current_step() < total_steps:
         sampler.set_epoch(epoch)
@@ -117,12 +129,16 @@ def main() -> None:
             loss = crit(ddp(x), y)
             loss.backward()       # gradients all-reduced across the live replica groups
             opt.step()            # only applied if the step committed
+            if prof is not None:
+                prof.step()
             if manager.current_step() % 10 == 0:
                 print(f"[{replica_group}] step={manager.current_step()} batches_committed={manager.batches_committed()} "
                       f"participants={manager.num_participants()} loss={loss.item():.4f}", flush=True)
             if manager.current_step() >= total_steps:
                 break
 
+    if prof is not None:
+        prof.stop()
     if out_path:
         torch.save({"model": {k: v.cpu() for k, v in m.state_dict().items()}, "step": manager.current_step()}, out_path)
     print(json.dumps({"replica_group": replica_group, "final_step": manager.current_step(),

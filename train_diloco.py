@@ -84,15 +84,27 @@ def main() -> None:
                 should_quantize=quantize and use_cuda, use_bucketization=True, bucket_cap_mb=32,
                 fragment_sync_delay=int(os.environ.get("SYNC_DELAY", 0)),
                 fragment_update_alpha=float(os.environ.get("ALPHA", 0.0))):
+        prof = None
+        if os.environ.get("PROFILE_DIR"):  # chrome traces incl. the torchft::local_sgd::* spans
+            from torch.profiler import ProfilerActivity, profile, schedule, tensorboard_trace_handler
+
+            acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if use_cuda else [])
+            prof = profile(activities=acts, schedule=schedule(wait=2, warmup=2, active=2 * sync_every, repeat=1),
+                           on_trace_ready=tensorboard_trace_handler(os.path.join(os.environ["PROFILE_DIR"], f"group{group}")))
+            prof.start()
         for i in range(steps):
             x = torch.randn(32, 64, generator=gen).to(device)
             inner.zero_grad()
             loss = (model(x) - x.flip(-1)).pow(2).mean()
             loss.backward()
             inner.step()  # hooks: prepare/perform the outer sync on schedule
+            if prof is not None:
+                prof.step()
             if (i + 1) % sync_every == 0:
                 print(f"[{group}] inner_step={i + 1} outer_step={manager.current_step()} "
                       f"participants={manager.num_participants()} loss={loss.item():.4f}", flush=True)
+        if prof is not None:
+            prof.stop()
     print(json.dumps({"replica_group": group, "outer_steps": manager.current_step()}), flush=True)
     manager.shutdown(wait=False)
     pg.shutdown()
