@@ -132,7 +132,8 @@ def main() -> None:
     rng = random.Random(a.seed)
     log_dir = a.log_dir or tempfile.mkdtemp(prefix="tft_orch_")
     os.makedirs(log_dir, exist_ok=True)
-    lighthouse = LighthouseServer(bind="127.0.0.1:0", min_replicas=a.min_replicas, join_timeout_ms=a.join_timeout_ms)
+    lighthouse = LighthouseServer(bind="127.0.0.1:0", min_replicas=a.min_replicas, join_timeout_ms=a.join_timeout_ms,
+                                  quorum_id_base=-1)  # clock-based ids: a restarted orchestrator never reuses one
     roles = hsdp(*a.script_args, replicas=a.replicas, workers_per_replica=a.workers_per_replica, max_restarts=0,
                  script=a.script, lighthouse=lighthouse.address(), gpus_per_node=a.gpus_per_node)
     groups: List[Group] = [Group(r, os.path.join(log_dir, f"{r.name}.port"), log_dir) for r in roles]

@@ -434,6 +434,38 @@ def test_native_selftest_under_sanitizers(sanitize, needle):
     assert r.returncode == 0
 
 
+def test_restarted_lighthouse_never_reuses_quorum_ids():
+    """quorum_id_base=-1 (CLI: --quorum_id_base auto): ids come from the clock, so a new incarnation starts above
+    everything the previous one handed out (process groups rendezvous under store prefixes keyed by quorum id)."""
+    ids = []
+    for _ in range(2):
+        lh = _C.LighthouseServer(bind="[::]:0", min_replicas=1, join_timeout_ms=50, quorum_tick_ms=10, quorum_id_base=-1)
+        try:
+            c = _C.LighthouseClient(lh.address(), timedelta(seconds=5))
+            first = c.quorum("a", timedelta(seconds=5)).quorum_id
+            # membership change -> bump
+            import threading
+
+            c.heartbeat("b", timedelta(seconds=1))  # known and healthy: "a" alone is no longer a majority
+            t = threading.Thread(target=lambda: _C.LighthouseClient(lh.address(), timedelta(seconds=5)).quorum("b", timedelta(seconds=5)))
+            t.start()
+            second = c.quorum("a", timedelta(seconds=5)).quorum_id
+            t.join()
+            assert second == first + 1
+            ids += [first, second]
+        finally:
+            lh.shutdown()
+        time.sleep(0.6)
+    assert ids == sorted(ids) and len(set(ids)) == 4 and ids[2] > ids[1]
+    assert ids[0] < 2 ** 31  # fits the 32-bit epoch field of the in-kernel flags
+    # default stays reference-compatible: first quorum has id 1
+    lh = _C.LighthouseServer(bind="[::]:0", min_replicas=1, join_timeout_ms=50)
+    try:
+        assert _C.LighthouseClient(lh.address(), timedelta(seconds=5)).quorum("a", timedelta(seconds=5)).quorum_id == 1
+    finally:
+        lh.shutdown()
+
+
 def test_status_json(lighthouse):
     import json
 

@@ -124,7 +124,8 @@ PYBIND11_MODULE(_C, m) {
 
   py::class_<Lighthouse>(m, "LighthouseServer")
       .def(py::init([](const std::string& bind, uint64_t min_replicas, std::optional<uint64_t> join_timeout_ms,
-                       std::optional<uint64_t> quorum_tick_ms, std::optional<uint64_t> heartbeat_timeout_ms) {
+                       std::optional<uint64_t> quorum_tick_ms, std::optional<uint64_t> heartbeat_timeout_ms,
+                       int64_t quorum_id_base) {
              LighthouseOpt o;
              o.bind = bind;
              o.min_replicas = min_replicas;
@@ -132,10 +133,12 @@ PYBIND11_MODULE(_C, m) {
              o.join_timeout_ms = join_timeout_ms.value_or(100);
              o.quorum_tick_ms = quorum_tick_ms.value_or(100);
              o.heartbeat_timeout_ms = heartbeat_timeout_ms.value_or(5000);
+             o.quorum_id_base = quorum_id_base;
              return std::make_unique<Lighthouse>(o);
            }),
            py::arg("bind"), py::arg("min_replicas"), py::arg("join_timeout_ms") = py::none(),
            py::arg("quorum_tick_ms") = py::none(), py::arg("heartbeat_timeout_ms") = py::none(),
+           py::arg("quorum_id_base") = 0,
            py::call_guard<py::gil_scoped_release>())
       .def("address", &Lighthouse::address)
       .def("shutdown", &Lighthouse::shutdown, py::call_guard<py::gil_scoped_release>());

@@ -14,7 +14,8 @@ namespace {
 void usage() {
   fprintf(stderr,
           "torchft_b200_lighthouse --min_replicas N [--bind [::]:29510] [--join_timeout_ms 60000]\n"
-          "                        [--quorum_tick_ms 100] [--heartbeat_timeout_ms 5000]\n");
+          "                        [--quorum_tick_ms 100] [--heartbeat_timeout_ms 5000]\n"
+          "                        [--quorum_id_base 0|auto|N]   (auto: clock-based, ids never repeat across restarts)\n");
 }
 }  // namespace
 
@@ -43,6 +44,7 @@ int run_lighthouse_cli(const std::vector<std::string>& args) {
       else if (k == "--join_timeout_ms") opt.join_timeout_ms = std::stoull(v);
       else if (k == "--quorum_tick_ms") opt.quorum_tick_ms = std::stoull(v);
       else if (k == "--heartbeat_timeout_ms") opt.heartbeat_timeout_ms = std::stoull(v);
+      else if (k == "--quorum_id_base") opt.quorum_id_base = (v == "auto") ? -1 : std::stoll(v);
       else {
         fprintf(stderr, "unknown flag %s\n", k.c_str());
         usage();

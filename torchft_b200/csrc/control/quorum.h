@@ -51,6 +51,12 @@ struct LighthouseOpt {
   uint64_t join_timeout_ms = 60000;
   uint64_t quorum_tick_ms = 100;
   uint64_t heartbeat_timeout_ms = 5000;
+  // First quorum gets id quorum_id_base + 1. A RESTARTED Lighthouse must not hand out ids that were
+  // already used (process groups rendezvous under ".../torchft/<quorum_id>/<rank>" in long-lived
+  // stores): -1 = quarter seconds since 2025-01-01 (fits the 32-bit epoch of the in-kernel flags until
+  // 2059), larger than anything a previous incarnation reached unless it averaged more than four quorum
+  // changes per second. 0 = the reference's behaviour.
+  int64_t quorum_id_base = 0;
 };
 
 struct ParticipantDetails {
