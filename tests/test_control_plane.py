@@ -446,9 +446,14 @@ def test_restarted_lighthouse_never_reuses_quorum_ids():
             # membership change -> bump
             import threading
 
-            c.heartbeat("b", timedelta(seconds=1))  # known and healthy: "a" alone is no longer a majority
             t = threading.Thread(target=lambda: _C.LighthouseClient(lh.address(), timedelta(seconds=5)).quorum("b", timedelta(seconds=5)))
             t.start()
+            from torchft_b200.coordination import lighthouse_status
+
+            deadline = time.time() + 5  # "b" alone is not a majority of {a, b}: it waits until "a" asks again
+            while "b" not in lighthouse_status(lh.address().replace("[::]", "127.0.0.1"))["waiting"]:
+                assert time.time() < deadline
+                time.sleep(0.01)
             second = c.quorum("a", timedelta(seconds=5)).quorum_id
             t.join()
             assert second == first + 1
