@@ -231,3 +231,48 @@ def test_chaos_soak_ends_with_identical_weights(tmp_path):
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     res = json.loads(out.read_text())
     assert res["pass"] and res["final_weights_identical"] and res["n_injected"] >= 1, res
+
+
+def test_slurm_runner_resubmits_only_dead_replica_groups(tmp_path):
+    """examples/slurm/runner.py against fake sbatch/squeue: every replica group is submitted once, a group that
+    disappears from the queue is re-submitted, live ones are left alone."""
+    import stat
+    import time
+
+    state = tmp_path / "queue.txt"
+    log = tmp_path / "sbatch.log"
+    state.write_text("")
+    (tmp_path / "sbatch").write_text(
+        "#!/bin/bash\n"
+        f"echo \"$@\" >> {log}\n"
+        "name=$(printf '%s\\n' \"$@\" | sed -n 's/^--job-name=//p')\n"
+        f"jid=$((1000 + $(wc -l < {log})))\n"
+        f"echo \"$name $jid\" >> {state}\n"
+        "echo $jid\n")
+    (tmp_path / "squeue").write_text(f"#!/bin/bash\ncat {state}\n")
+    for f in ("sbatch", "squeue"):
+        os.chmod(tmp_path / f, os.stat(tmp_path / f).st_mode | stat.S_IEXEC)
+    env = dict(os.environ, PATH=f"{tmp_path}:{os.environ['PATH']}")
+    p = subprocess.Popen([sys.executable, os.path.join(ROOT, "examples/slurm/runner.py"), "--replicas", "3", "--check-every", "0.2",
+                          "--job-name", "tft", "--script", "train.py", "--lighthouse", "http://lh:1"],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        deadline = time.time() + 20
+        while len(state.read_text().splitlines()) < 3 and time.time() < deadline:
+            time.sleep(0.05)
+        time.sleep(0.6)  # a few more polls: nothing new may be submitted while all three are alive
+        assert len(log.read_text().splitlines()) == 3
+        first = log.read_text().splitlines()[1]
+        assert "--job-name=tft_1" in first and "REPLICA_GROUP_ID=1,NUM_REPLICA_GROUPS=3,TORCHFT_LIGHTHOUSE=http://lh:1" in first
+        assert "--master_port=29601 train.py" in first
+        # replica group 1 dies (leaves the queue): only that one comes back
+        state.write_text("".join(l + "\n" for l in state.read_text().splitlines() if not l.startswith("tft_1 ")))
+        deadline = time.time() + 20
+        while len(log.read_text().splitlines()) < 4 and time.time() < deadline:
+            time.sleep(0.05)
+        time.sleep(0.5)
+        lines = log.read_text().splitlines()
+        assert len(lines) == 4 and "--job-name=tft_1" in lines[3]
+    finally:
+        p.kill()
+        p.wait()
