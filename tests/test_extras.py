@@ -276,3 +276,35 @@ def test_slurm_runner_resubmits_only_dead_replica_groups(tmp_path):
     finally:
         p.kill()
         p.wait()
+
+
+def test_punisher_kills_a_replica_through_the_lighthouse(tmp_path):
+    """examples/slurm/punisher.py kill_one -> Lighthouse /status.json -> POST /replica/<id>/kill -> ManagerServer.Kill RPC
+    -> the victim process exits with code 1 (the reference's dashboard Kill button does the same)."""
+    from datetime import timedelta
+
+    from torchft_b200.bench_utils import loopback
+    from torchft_b200.coordination import LighthouseServer
+
+    lh = LighthouseServer(bind="[::]:0", min_replicas=1, join_timeout_ms=100, quorum_tick_ms=10)
+    addr = loopback(lh.address())
+    victim_code = (
+        "import sys, time; sys.path.insert(0, %r)\n"
+        "from datetime import timedelta\n"
+        "from torchft_b200.coordination import ManagerServer, ManagerClient\n"
+        "T = timedelta(seconds=10)\n"
+        "ms = ManagerServer(replica_id='victim', lighthouse_addr=%r, hostname='127.0.0.1', bind='127.0.0.1:0', store_addr='s:1',\n"
+        "                   world_size=1, heartbeat_interval=timedelta(milliseconds=50), connect_timeout=T, quorum_retries=0)\n"
+        "ManagerClient(ms.address(), T)._quorum(0, 3, '', False, T, 0, True)\n"
+        "print('joined', flush=True); time.sleep(60)\n" % (ROOT, addr))
+    p = subprocess.Popen([sys.executable, "-c", victim_code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        assert p.stdout.readline().strip() == "joined"
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "examples/slurm/punisher.py"), "kill_one", "--lighthouse", addr],
+                           capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert p.wait(20) == 1
+    finally:
+        if p.poll() is None:
+            p.kill()
+        lh.shutdown()
