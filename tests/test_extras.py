@@ -225,8 +225,8 @@ def test_chaos_soak_ends_with_identical_weights(tmp_path):
 
     out = tmp_path / "soak.json"
     env = dict(os.environ, USE_CPU="1", CUDA_VISIBLE_DEVICES="")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench/chaos_soak.py"), "--steps", "300", "--mtbf-secs", "8",
-                        "--failures", "kill_proc,comms,kill_group", "--min-replicas", "2", "--max-failures", "2", "--timeout", "240", "--out", str(out)],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench/chaos_soak.py"), "--steps", "200", "--mtbf-secs", "5",
+                        "--failures", "kill_proc,comms,kill_group", "--min-replicas", "2", "--max-failures", "1", "--timeout", "240", "--out", str(out)],
                        env=env, capture_output=True, text=True, timeout=270)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
     res = json.loads(out.read_text())
