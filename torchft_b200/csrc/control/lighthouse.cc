@@ -1,3 +1,8 @@
+// Lighthouse server: heartbeat table, participants of the in-flight round, tick loop, quorum broadcast,
+// dashboard + kill endpoint. Behavioural reference: src/lighthouse.rs (State :57-66, _quorum_tick :292-343,
+// RPC quorum :484-551 incl. "a quorum request counts as a heartbeat", heartbeat :553-566, get_status :415-452,
+// kill :454-479). Differences: waiters replay missed generations from a short history (the reference uses a
+// tokio broadcast channel), the dashboard is plain JS polling /status, and /status.json + quorum_id_base exist.
 #include "lighthouse.h"
 
 #include <algorithm>

@@ -1,3 +1,7 @@
+// Pure decision procedures + message codecs. Reference semantics: quorum_compute src/lighthouse.rs:141-269,
+// quorum_changed :133-138, compute_quorum_results src/manager.rs:489-625 (recovery assignment: up-to-date
+// replicas serve the stragglers round-robin, offset by group rank; primary store = group_rank % n-th
+// up-to-date replica; init_sync forces everybody but the primary to heal at step 0).
 #include "quorum.h"
 
 #include <algorithm>

@@ -1,3 +1,5 @@
+// Thread-per-connection RPC server/client over the framed protocol of wire.h (the reference gets this layer from
+// tonic/hyper: src/net.rs:16-42 connect + keep-alive, src/timeout.rs:26-69 server-side deadlines).
 // Thread-per-connection RPC/HTTP server base and the blocking RPC client.
 #pragma once
 
