@@ -1,6 +1,7 @@
 """Checkpoint transports: generic multi-node recovery scenario (threads + barriers) run against
 HTTP (full and chunked) and PG (gloo) transports; RWLock semantics; step mismatch and timeouts."""
 
+import os
 import copy
 import threading
 import time
@@ -178,3 +179,66 @@ def test_rwlock_writer_preference():
     tw.join()
     tr.join()
     assert got == ["w", "r"]
+
+
+# ------------------------------------------------------------- durable checkpoints
+class _FakeManager:
+    def __init__(self, rank=0):
+        self.step, self.batches, self.rank, self._group_rank = 0, 0, rank, 0
+
+    def current_step(self):
+        return self.step
+
+    def participating_rank(self):
+        return self.rank
+
+    def state_dict(self):
+        return {"step": self.step, "batches_committed": self.batches}
+
+    def load_state_dict(self, sd):
+        self.step, self.batches = sd["step"], sd["batches_committed"]
+
+
+def test_durable_checkpointer_roundtrip_rotation_and_torn_files(tmp_path):
+    from torchft_b200.checkpointing import DurableCheckpointer
+
+    w = torch.zeros(4)
+    mgr = _FakeManager()
+    ck = DurableCheckpointer(mgr, state_dict=lambda: {"w": w, "note": "hi"}, load_state_dict=lambda sd: w.copy_(sd["w"]),
+                             directory=str(tmp_path), every_n_steps=2, keep=2)
+    assert ck.restore() is None  # fresh run
+    for step in range(1, 9):
+        w += 1
+        mgr.step, mgr.batches = step, 2 * step
+        started = ck.maybe_save()
+        assert started == (step % 2 == 0)
+        w_snapshot = w.clone()
+        w += 100  # mutate right after: the snapshot was taken synchronously
+        ck.wait()
+        w.copy_(w_snapshot)
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".pt"))
+    assert files == ["step_6.rank_0.pt", "step_8.rank_0.pt"]  # keep=2
+    assert (tmp_path / "LATEST.rank_0").read_text() == "step_8.rank_0.pt"
+    # restore into a fresh process image
+    w.zero_()
+    mgr2 = _FakeManager()
+    ck2 = DurableCheckpointer(mgr2, state_dict=lambda: {"w": w}, load_state_dict=lambda sd: w.copy_(sd["w"]), directory=str(tmp_path))
+    assert ck2.restore() == 8 and mgr2.step == 8 and mgr2.batches == 16 and torch.equal(w, torch.full((4,), 8.0))
+    # a torn newest file is skipped in favour of the previous checkpoint
+    with open(tmp_path / "step_8.rank_0.pt", "r+b") as f:
+        f.truncate(10)
+    w.zero_()
+    assert ck2.restore() == 6 and torch.equal(w, torch.full((4,), 6.0))
+    # only the participant with replica rank 0 writes; spares / healing replicas (rank None) do not
+    for rank in (1, None):
+        other = DurableCheckpointer(_FakeManager(rank), state_dict=lambda: {}, load_state_dict=lambda sd: None,
+                                    directory=str(tmp_path / f"r{rank}"), every_n_steps=1)
+        other._manager.step = 3
+        assert other.maybe_save() is False and other.latest_step() is None
+    # a failed write is reported on the next call instead of being lost
+    bad = DurableCheckpointer(mgr, state_dict=lambda: {"f": (lambda: 0)}, load_state_dict=lambda sd: None,
+                              directory=str(tmp_path / "bad"), every_n_steps=1)
+    mgr.step = 9
+    assert bad.maybe_save()
+    with pytest.raises(RuntimeError, match="durable checkpoint write failed"):
+        bad.wait()

@@ -98,6 +98,15 @@ def main() -> None:
     ddp = DistributedDataParallel(manager, m)
     opt = Optimizer(manager, inner)
     crit = nn.CrossEntropyLoss()
+    # CKPT_DIR=/shared/dir: durable checkpoints for whole-job restarts (live healing covers partial failures)
+    ckpt = None
+    if os.environ.get("CKPT_DIR"):
+        from torchft_b200.checkpointing import DurableCheckpointer
+
+        ckpt = DurableCheckpointer(manager, state_dict=state_dict, load_state_dict=load_state_dict,
+                                   directory=os.environ["CKPT_DIR"], every_n_steps=int(os.environ.get("CKPT_EVERY", 50)))
+        resumed = ckpt.restore()
+        print(f"[{replica_group}] resumed_from_step={resumed}", flush=True)
     injector = None
     if os.environ.get("TORCHFT_FAILURE_PORT_FILE"):  # chaos testing (examples/orchestrator)
         from torchft_b200.failure import FailureInjector
@@ -131,6 +140,8 @@ def main() -> None:
             opt.step()            # only applied if the step committed
             if prof is not None:
                 prof.step()
+            if ckpt is not None:
+                ckpt.maybe_save()
             if manager.current_step() % 10 == 0:
                 print(f"[{replica_group}] step={manager.current_step()} batches_committed={manager.batches_committed()} "
                       f"participants={manager.num_participants()} loss={loss.item():.4f}", flush=True)
@@ -139,6 +150,9 @@ def main() -> None:
 
     if prof is not None:
         prof.stop()
+    if ckpt is not None:
+        ckpt.maybe_save(force=True)
+        ckpt.wait()
     if out_path:
         torch.save({"model": {k: v.cpu() for k, v in m.state_dict().items()}, "step": manager.current_step()}, out_path)
     print(json.dumps({"replica_group": replica_group, "final_step": manager.current_step(),
