@@ -193,6 +193,33 @@ def test_jsonl_event_sink(tmp_path, monkeypatch):
     assert rec["logger"] == "torchft_test_events" and rec["quorum_id"] == 3 and rec["step"] == 9 and rec["replica_id"] == "r0"
 
 
+def test_prometheus_sink_counts_quorums_commits_errors(monkeypatch):
+    import socket
+    import urllib.request
+
+    from torchft_b200 import otel
+
+    pytest.importorskip("prometheus_client")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    monkeypatch.setenv(otel.PROMETHEUS_PORT_ENV, str(port))
+    for name in ("torchft_quorums", "torchft_commits", "torchft_errors"):
+        otel.setup_logger(name)
+    base = {"job_id": "j", "replica_id": "r7", "rank": 0}
+    logging.getLogger("torchft_quorums").info("", extra=dict(base, quorum_id=5, step=11))
+    for ok in (True, True, False):
+        logging.getLogger("torchft_commits").info("", extra=dict(base, quorum_id=5, step=12, commit_result=ok))
+    logging.getLogger("torchft_errors").info("", extra=dict(base, quorum_id=5, error="boom"))
+    text = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=5).read().decode()
+    otel.shutdown()
+    assert 'torchft_quorum_changes_total{rank="0",replica_id="r7"} 1.0' in text
+    assert 'torchft_commits_total{rank="0",replica_id="r7",result="committed"} 2.0' in text
+    assert 'torchft_commits_total{rank="0",replica_id="r7",result="failed"} 1.0' in text
+    assert 'torchft_errors_total{rank="0",replica_id="r7"} 1.0' in text
+    assert 'torchft_step{rank="0",replica_id="r7"} 12.0' in text and 'torchft_quorum_id{rank="0",replica_id="r7"} 5.0' in text
+
+
 def test_otel_requested_but_missing_raises(monkeypatch):
     from torchft_b200 import otel
 

@@ -11,6 +11,9 @@ Two sinks, both opt-in through the environment:
 * ``TORCHFT_B200_EVENTS_JSONL=/path/file.jsonl`` -- dependency-free JSON-lines sink
   (one object per quorum / commit / error event with job_id, replica_id, rank,
   quorum_id, step, ...), handy on air-gapped clusters and in tests.
+* ``TORCHFT_B200_PROMETHEUS_PORT=9400`` -- a Prometheus scrape endpoint fed by the same three loggers
+  (ours; needs ``prometheus_client``): ``torchft_quorum_changes_total``, ``torchft_commits_total{result=}``,
+  ``torchft_errors_total``, ``torchft_step``, ``torchft_quorum_id``, all labelled with ``replica_id`` / ``rank``.
 """
 
 from __future__ import annotations
@@ -25,6 +28,7 @@ from typing import Any, Dict
 TORCHFT_OTEL_RESOURCE_ATTRIBUTES_JSON = "TORCHFT_OTEL_RESOURCE_ATTRIBUTES_JSON"
 TORCHFT_USE_OTEL = "TORCHFT_USE_OTEL"
 EVENTS_JSONL_ENV = "TORCHFT_B200_EVENTS_JSONL"
+PROMETHEUS_PORT_ENV = "TORCHFT_B200_PROMETHEUS_PORT"
 
 _PROVIDERS: Dict[str, Any] = {}
 _JSONL: Dict[str, logging.Handler] = {}
@@ -53,6 +57,60 @@ class JsonLinesHandler(logging.Handler):
                 f.write(json.dumps(event) + "\n")
         except Exception:  # pragma: no cover
             self.handleError(record)
+
+
+class PrometheusHandler(logging.Handler):
+    """Turns quorum / commit / error records into Prometheus counters and gauges (one registry per process)."""
+
+    _lock = threading.Lock()
+    _metrics: Dict[str, Any] = {}
+    _server_port: Any = None
+
+    @classmethod
+    def _ensure(cls, port: int) -> Dict[str, Any]:
+        with cls._lock:
+            if not cls._metrics:
+                try:
+                    import prometheus_client as pc
+                except ImportError as e:
+                    raise RuntimeError(f"{PROMETHEUS_PORT_ENV} is set but prometheus_client is not installed: {e}") from e
+                labels = ["replica_id", "rank"]
+                cls._metrics = {
+                    "quorums": pc.Counter("torchft_quorum_changes_total", "quorum reconfigurations seen by this rank", labels),
+                    "commits": pc.Counter("torchft_commits_total", "should_commit verdicts", labels + ["result"]),
+                    "errors": pc.Counter("torchft_errors_total", "process-group errors / aborts", labels),
+                    "step": pc.Gauge("torchft_step", "last step seen in a quorum or commit event", labels),
+                    "quorum_id": pc.Gauge("torchft_quorum_id", "current quorum id", labels),
+                }
+                if port > 0:
+                    pc.start_http_server(port)
+                    cls._server_port = port
+            return cls._metrics
+
+    def __init__(self, logger_name: str, port: int) -> None:
+        super().__init__(level=logging.NOTSET)
+        self._name = logger_name
+        self._m = self._ensure(port)
+
+    def emit(self, record: logging.LogRecord) -> None:
+        try:
+            d = record.__dict__
+            lab = {"replica_id": str(d.get("replica_id", "")), "rank": str(d.get("rank", ""))}
+            if self._name == "torchft_quorums":
+                self._m["quorums"].labels(**lab).inc()
+            elif self._name == "torchft_commits":
+                self._m["commits"].labels(result="committed" if d.get("commit_result") else "failed", **lab).inc()
+            elif self._name == "torchft_errors":
+                self._m["errors"].labels(**lab).inc()
+            if isinstance(d.get("step"), int):
+                self._m["step"].labels(**lab).set(d["step"])
+            if isinstance(d.get("quorum_id"), int):
+                self._m["quorum_id"].labels(**lab).set(d["quorum_id"])
+        except Exception:  # pragma: no cover
+            self.handleError(record)
+
+
+_PROM: Dict[str, logging.Handler] = {}
 
 
 def _setup_otel(name: str) -> None:
@@ -88,6 +146,13 @@ def setup_logger(name: str) -> None:
         if logger.level == logging.NOTSET or logger.level > logging.INFO:
             logger.setLevel(logging.INFO)
         _JSONL[name] = h
+    port = os.environ.get(PROMETHEUS_PORT_ENV)
+    if port and name not in _PROM:
+        h = PrometheusHandler(name, int(port))
+        logger.addHandler(h)
+        if logger.level == logging.NOTSET or logger.level > logging.INFO:
+            logger.setLevel(logging.INFO)
+        _PROM[name] = h
     if os.environ.get(TORCHFT_USE_OTEL, "false") != "false" and name not in _PROVIDERS:
         _setup_otel(name)
 
@@ -99,3 +164,6 @@ def shutdown() -> None:
     for name, h in _JSONL.items():
         logging.getLogger(name).removeHandler(h)
     _JSONL.clear()
+    for name, h in _PROM.items():
+        logging.getLogger(name).removeHandler(h)
+    _PROM.clear()
