@@ -294,3 +294,26 @@ def test_reference_import_paths_resolve():
                  "ProcessGroupBabyGloo", "ProcessGroupBabyNCCL", "ManagedProcessGroup", "WorldSizeMode"):
         assert hasattr(torchft_b200, name), name
     assert ProcessGroupBabyGloo is torchft_b200.ProcessGroupBabyGloo
+
+
+def test_doctor_reports_and_exit_code():
+    import subprocess
+    import sys
+
+    from torchft_b200 import doctor
+    from torchft_b200.coordination import LighthouseServer
+
+    lh = LighthouseServer(bind="127.0.0.1:0", min_replicas=3)
+    try:
+        checks = doctor.run(lighthouse=lh.address())
+    finally:
+        lh.shutdown()
+    by_name = {n: (lvl, d) for lvl, n, d in checks}
+    assert by_name["extension _C"][0] == "OK" and by_name["extension _K"][0] == "OK"
+    assert by_name["lighthouse"][0] == "OK" and "min_replicas=3" in by_name["lighthouse"][1]
+    if not torch.cuda.is_available():
+        assert by_name["cuda"][0] == "WARN"
+        r = subprocess.run([sys.executable, "-m", "torchft_b200.doctor", "--require-gpu"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1 and "[FAIL] cuda" in r.stdout
+    # an unreachable lighthouse is a FAIL line, not a crash
+    assert dict((n, lvl) for lvl, n, _ in doctor.run(lighthouse="http://127.0.0.1:9"))["lighthouse"] == "FAIL"
