@@ -314,7 +314,9 @@ def test_manager_should_commit_barrier(lighthouse):
         ms.shutdown()
 
 
-def test_manager_quorum_heal_first_step_and_metadata(lighthouse):
+def test_manager_quorum_heal_first_step_and_metadata():
+    # min_replicas=2: the quorum must contain BOTH groups no matter how the two requests are scheduled
+    lighthouse = _C.LighthouseServer(bind="[::]:0", min_replicas=2, join_timeout_ms=100, quorum_tick_ms=10)
     m0, m1 = _manager(lighthouse, "rep_0"), _manager(lighthouse, "rep_1")
     try:
         res = {}
@@ -339,6 +341,7 @@ def test_manager_quorum_heal_first_step_and_metadata(lighthouse):
     finally:
         m0.shutdown()
         m1.shutdown()
+        lighthouse.shutdown()
 
 
 def test_manager_quorum_group_barrier_times_out(lighthouse):

@@ -25,7 +25,10 @@ Lighthouse::Lighthouse(LighthouseOpt opt) : opt_(std::move(opt)) {
   if (opt_.quorum_id_base < 0) opt_.quorum_id_base = (unix_ms() - 1735689600000ll) / 250;  // quarter seconds since 2025-01-01
   state_.quorum_id = opt_.quorum_id_base;
   start(opt_.bind, "tft-lighths");
-  tick_thread_ = std::thread([this] { tick_loop(); });
+  tick_thread_ = std::thread([this] {
+    name_this_thread("tft-lighths-tick");
+    tick_loop();
+  });
 }
 
 Lighthouse::~Lighthouse() { shutdown(); }

@@ -32,7 +32,10 @@ ManagerServer::ManagerServer(std::string replica_id, std::string lighthouse_addr
   // fail construction if the lighthouse is unreachable within connect_timeout
   lh_client_ = std::make_shared<LighthouseClient>(lighthouse_addr_, connect_timeout_);
   start(bind, "tft-manager");
-  heartbeat_thread_ = std::thread([this] { heartbeat_loop(); });
+  heartbeat_thread_ = std::thread([this] {
+    name_this_thread("tft-manager-hb");
+    heartbeat_loop();
+  });
 }
 
 ManagerServer::~ManagerServer() { shutdown(); }
@@ -187,7 +190,10 @@ uint32_t ManagerServer::handle_rpc(uint32_t method, const std::string& req, Time
         participants_.clear();
         const uint64_t round = ++active_round_;
         ++quorum_workers_;
-        std::thread([this, me, timeout, round] { run_quorum(me, timeout, round); }).detach();
+        std::thread([this, me, timeout, round] {
+          name_this_thread("tft-manager-q");
+          run_quorum(me, timeout, round);
+        }).detach();
       }
       while (quorum_gen_ <= seen) {
         if (shutdown_) {

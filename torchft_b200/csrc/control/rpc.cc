@@ -12,9 +12,13 @@ namespace tft {
 
 RpcServer::~RpcServer() { stop(); }
 
-void RpcServer::start(const std::string& bind, const std::string& /*thread_name*/) {
+void RpcServer::start(const std::string& bind, const std::string& thread_name) {
   listen_fd_ = listen_on(bind, &port_);
-  accept_thread_ = std::thread([this] { accept_loop(); });
+  thread_name_ = thread_name;
+  accept_thread_ = std::thread([this] {
+    name_this_thread(thread_name_ + "-acc");
+    accept_loop();
+  });
 }
 
 void RpcServer::stop() {
@@ -51,6 +55,7 @@ void RpcServer::accept_loop() {
       ++workers_;
     }
     std::thread([this, fd] {
+      name_this_thread(thread_name_ + "-conn");
       try {
         serve(fd);
       } catch (...) {

@@ -51,6 +51,7 @@ class RpcServer {
   int listen_fd_ = -1;
   int port_ = 0;
   std::thread accept_thread_;
+  std::string thread_name_;
   std::atomic<bool> stopping_{false};
   std::mutex mu_;
   std::condition_variable cv_;

@@ -1,5 +1,7 @@
 #include "wire.h"
 
+#include <pthread.h>
+
 #include <arpa/inet.h>
 #include <errno.h>
 #include <fcntl.h>
@@ -219,6 +221,10 @@ bool send_all(int fd, const void* buf, size_t n, TimePoint deadline, bool* timed
 }
 bool recv_all(int fd, void* buf, size_t n, TimePoint deadline, bool* timed_out) {
   return io_all(fd, buf, n, deadline, false, timed_out);
+}
+
+void name_this_thread(const std::string& name) {
+  pthread_setname_np(pthread_self(), name.substr(0, 15).c_str());
 }
 
 void close_fd(int fd) {

@@ -138,6 +138,8 @@ int connect_with_backoff(const std::string& addr, TimePoint deadline);
 bool send_all(int fd, const void* buf, size_t n, TimePoint deadline, bool* timed_out = nullptr);
 bool recv_all(int fd, void* buf, size_t n, TimePoint deadline, bool* timed_out = nullptr);
 
+// Name the calling thread (<= 15 chars shown by top -H / gdb / py-spy); reference: tokio thread names, src/lib.rs:105,166,500,635.
+void name_this_thread(const std::string& name);
 void close_fd(int fd);
 void shutdown_fd(int fd);
 std::string local_hostname();
