@@ -470,3 +470,77 @@ def test_managed_work_lazy_callbacks(client_cls):
             f1.value()
     finally:
         h.close()
+
+
+class _FailingWork(DummyWork):
+    """Inner work whose wait() raises (a collective that failed after launch)."""
+
+    def wait(self, timeout=None):  # type: ignore[override]
+        raise RuntimeError("inner collective failed")
+
+
+def test_managed_work_wait_never_raises_and_reports(client_cls):
+    from torchft_b200.manager import _ManagedWork
+
+    h = Harness(client_cls)
+    m = h.manager
+    try:
+        t = torch.tensor([1.0])
+        w = _ManagedWork(m, _FailingWork(t), t)
+        assert m.errored() is None
+        assert w.wait() is False          # swallowed ...
+        assert m.errored() is not None    # ... but latched: this step will not commit
+        assert "inner collective failed" in str(m.errored().original_exception)
+    finally:
+        h.close()
+
+
+def test_managed_work_callback_exception_falls_back_to_default(client_cls):
+    from torchft_b200.manager import _ManagedWork
+
+    h = Harness(client_cls)
+    m = h.manager
+    try:
+        t = torch.tensor([4.0])
+        w = _ManagedWork(m, DummyWork(t), t)
+        order = []
+
+        def boom(f):
+            order.append("boom")
+            raise ValueError("callback exploded")
+
+        fut = w.get_future().then(lambda f: (order.append("first"), f.value() + 1)[1]).then(boom).then(
+            lambda f: order.append("never"))
+        assert w.wait() is True           # the pipeline's failure is swallowed by wrap_future ...
+        assert order == ["first", "boom"]  # ... later callbacks do not run
+        assert fut.wait() is t            # ... and the future resolves to the default (the original tensor)
+        assert "callback exploded" in str(m.errored().original_exception)
+    finally:
+        h.close()
+
+
+def test_managed_work_other_entry_points_materialize_the_pipeline(client_cls):
+    from torchft_b200.manager import _ManagedWork
+
+    h = Harness(client_cls)
+    m = h.manager
+    try:
+        for entry in ("block_current_stream", "synchronize"):
+            t = torch.tensor([2.0])
+            ran = []
+            w = _ManagedWork(m, DummyWork(t), t)
+            fut = w.get_future().then(lambda f: (ran.append(1), f.value() * 3)[1])
+            getattr(w, entry)()
+            assert ran == [1], entry      # callbacks ran without an explicit wait()
+            assert fut.wait().item() == 6.0
+            assert ran == [1]             # and only once
+        # callbacks registered on different handles of the same work run in registration order
+        t = torch.tensor([1.0])
+        w = _ManagedWork(m, DummyWork(t), t)
+        seq = []
+        w.get_future().then(lambda f: seq.append("x") or f.value())
+        w.get_future().then(lambda f: seq.append("y") or f.value())
+        w.wait()
+        assert seq == ["x", "y"]
+    finally:
+        h.close()

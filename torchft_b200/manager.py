@@ -806,9 +806,9 @@ class _ManagedWork(Work):
         self._assert_same_stream()
         with get_stream_context(self._stream):
             blk = getattr(self._inner, "block_current_stream", None)
-            if blk is not None:
+            if blk is not None and self._stream is not None:
                 blk()
-            else:
+            else:  # no accelerator stream to block: fall back to a host wait
                 self._inner.wait()
         self._materialize()
 
