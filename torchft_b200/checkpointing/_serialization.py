@@ -30,4 +30,8 @@ def streaming_save(obj: Any, f: IO[bytes]) -> None:
 def streaming_load(f: IO[bytes]) -> Any:
     if _HAS_STREAMING:
         return _streaming_load(f, weights_only=False)
+    if not (hasattr(f, "seekable") and f.seekable()):  # torch.load needs a seekable file
+        import io
+
+        f = io.BytesIO(f.read())
     return torch.load(f, weights_only=False)

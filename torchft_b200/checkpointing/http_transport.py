@@ -110,12 +110,20 @@ class HTTPTransport(CheckpointTransport[T], Generic[T]):
                     with transport._lock.r_lock():
                         if step != transport._step:
                             return self._fail(400, f"invalid checkpoint requested: serving {transport._step} but got {step}")
-                        payload = transport._payload(parts[2])
+                        # Stream straight from the staged tensors into the socket: no whole-payload buffer on
+                        # the sender (a 16 GB state would otherwise exist three times). The body is delimited
+                        # by connection close, so a failure mid-stream surfaces as a truncated read.
                         self.send_response(200)
                         self.send_header("Content-Type", "application/octet-stream")
-                        self.send_header("Content-Length", str(len(payload)))
+                        self.send_header("Connection", "close")
                         self.end_headers()
-                        self.wfile.write(payload)
+                        self.close_connection = True
+                        out = io.BufferedWriter(self.wfile, buffer_size=4 << 20)  # type: ignore[arg-type]
+                        try:
+                            transport._write_payload(parts[2], out)
+                            out.flush()
+                        finally:
+                            out.detach()  # the wrapper must not close the handler's wfile when it is collected
                 except TimeoutError as e:
                     self._fail(503, f"checkpoint not available: {e}")
                 except (BrokenPipeError, ConnectionResetError):
@@ -132,19 +140,16 @@ class HTTPTransport(CheckpointTransport[T], Generic[T]):
         self._thread.start()
 
     # ------------------------------------------------------------ server side
-    def _payload(self, what: str) -> bytes:
+    def _write_payload(self, what: str, out: Any) -> None:
         state = self._state
-        buf = io.BytesIO()
         if what == "full":
-            streaming_save(state, buf)
+            streaming_save(state, out)
+            return
+        leaves, spec = pytree.tree_flatten(state)
+        if what == "metadata":
+            pickle.dump({"treespec": spec, "num_leaves": len(leaves), "num_chunks": self._num_chunks}, out)
         else:
-            leaves, spec = pytree.tree_flatten(state)
-            if what == "metadata":
-                pickle.dump({"treespec": spec, "num_leaves": len(leaves), "num_chunks": self._num_chunks}, buf)
-            else:
-                i = int(what)
-                streaming_save(leaves[i :: max(self._num_chunks, 1)], buf)
-        return buf.getvalue()
+            streaming_save(leaves[int(what) :: max(self._num_chunks, 1)], out)
 
     def address(self) -> str:
         port = self._server.socket.getsockname()[1]
@@ -182,15 +187,20 @@ class HTTPTransport(CheckpointTransport[T], Generic[T]):
         with urllib.request.urlopen(url, timeout=timeout.total_seconds()) as r:
             return r.read()
 
+    def _load(self, url: str, timeout: timedelta) -> Any:
+        """Deserialise while the bytes arrive (tensors are filled straight from the socket)."""
+        with urllib.request.urlopen(url, timeout=timeout.total_seconds()) as r:
+            return streaming_load(io.BufferedReader(r, buffer_size=4 << 20))  # type: ignore[arg-type]
+
     def recv_checkpoint(self, src_rank: int, metadata: str, step: int, timeout: timedelta) -> T:
         base = f"{metadata}{step}"
         try:
             if self._num_chunks <= 0:
-                return streaming_load(io.BytesIO(self._get(f"{base}/full", timeout)))
+                return self._load(f"{base}/full", timeout)
             meta = pickle.loads(self._get(f"{base}/metadata", timeout))
             n = max(int(meta["num_chunks"]), 1)
             with ThreadPoolExecutor(max_workers=n, thread_name_prefix="tft_http_recv") as ex:
-                parts = list(ex.map(lambda i: streaming_load(io.BytesIO(self._get(f"{base}/{i}", timeout))), range(n)))
+                parts = list(ex.map(lambda i: self._load(f"{base}/{i}", timeout), range(n)))
             leaves: List[Any] = [None] * int(meta["num_leaves"])
             for i, chunk in enumerate(parts):
                 leaves[i::n] = chunk
