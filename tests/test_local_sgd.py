@@ -205,7 +205,10 @@ def test_streaming_diloco_fragment_schedule():
 
 
 # ------------------------------------------------------------------ integration
-def _replica(lh_addr: str, rid: int, algo: str, steps: int, fail_allreduce_at: int, out: Dict[int, Any], use_quant=False):
+def _replica(lh_addr: str, rid: int, algo: str, steps: int, fail_allreduce_at: int, out: Dict[int, Any], use_quant=False,
+             start_after=None, signal_at=None):
+    if start_after is not None:  # late joiner (upscale scenario)
+        assert start_after.wait(60)
     store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
     torch.manual_seed(100 + rid)
     model = SimpleModel()
@@ -231,6 +234,8 @@ def _replica(lh_addr: str, rid: int, algo: str, steps: int, fail_allreduce_at: i
                 inner.zero_grad()
                 model(torch.rand(4, 3, generator=gen)).mean().backward()
                 inner.step()
+                if signal_at is not None and manager.current_step() >= signal_at[0]:
+                    signal_at[1].set()
             res = {"params": _params(model), "step": manager.current_step()}
             if algo == "diloco":
                 res["original"] = {n: t.clone() for n, t in algo_obj._fragments[0].original_parameters.items()}
@@ -261,3 +266,35 @@ def test_integration_two_replicas(algo, fail_at):
         s0, s1 = out[0]["outer"]["state"], out[1]["outer"]["state"]
         for k in s0:
             torch.testing.assert_close(s0[k]["momentum_buffer"], s1[k]["momentum_buffer"])
+
+
+@pytest.mark.parametrize("algo", ["local_sgd", "diloco"])
+def test_integration_upscale_third_replica_joins(algo):
+    """Two replicas sync for a while, a third joins at outer step 2 (reference: local_sgd_integ_test 'upscale'). The healing
+    payload must carry the algorithm's own state too (DiLoCo: backup weights + outer optimizer, registered with the Manager),
+    so that all three end with identical global state."""
+    import threading
+
+    lh = LighthouseServer(bind="[::]:0", min_replicas=2, join_timeout_ms=300)
+    out: Dict[int, Any] = {}
+    go = threading.Event()
+    steps = 6
+    try:
+        with ThreadPoolExecutor(max_workers=3) as ex:
+            futs = [ex.submit(_replica, lh.address(), 0, algo, steps, -1, out, False, None, (2, go)),
+                    ex.submit(_replica, lh.address(), 1, algo, steps, -1, out),
+                    ex.submit(_replica, lh.address(), 2, algo, steps, -1, out, False, go, None)]
+            for f in futs:
+                f.result(timeout=180)
+    finally:
+        lh.shutdown()
+    assert out[0]["step"] == out[1]["step"] == out[2]["step"] == steps
+    key = "original" if algo == "diloco" else "params"
+    for r in (1, 2):
+        for n in out[0][key]:
+            torch.testing.assert_close(out[0][key][n], out[r][key][n])
+    if algo == "diloco":
+        for r in (1, 2):
+            s0, sr = out[0]["outer"]["state"], out[r]["outer"]["state"]
+            for k in s0:
+                torch.testing.assert_close(s0[k]["momentum_buffer"], sr[k]["momentum_buffer"])
