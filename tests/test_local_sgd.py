@@ -298,3 +298,72 @@ def test_integration_upscale_third_replica_joins(algo):
             s0, sr = out[0]["outer"]["state"], out[r]["outer"]["state"]
             for k in s0:
                 torch.testing.assert_close(s0[k]["momentum_buffer"], sr[k]["momentum_buffer"])
+
+
+class _Crash(Exception):
+    pass
+
+
+def _streaming_replica(lh_addr: str, rid: int, steps: int, crash_at: int, out: Dict[int, Any], attempts: Dict[int, int]):
+    """Streaming DiLoCo (2 fragments, staggered syncs) replica that can crash once and restart from scratch."""
+    for attempt in range(2):
+        attempts[rid] = attempt + 1
+        store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
+        torch.manual_seed(200 + rid)
+        f1, f2 = nn.Linear(3, 4), nn.Linear(4, 2)
+        model = nn.Sequential(f1, nn.ReLU(), f2)
+        pg = ProcessGroupGloo(timeout=timedelta(seconds=10))
+        inner = optim.SGD(model.parameters(), lr=0.05)
+        outers = [optim.SGD(f1.parameters(), lr=0.7, momentum=0.9, nesterov=True),
+                  optim.SGD(f2.parameters(), lr=0.7, momentum=0.9, nesterov=True)]
+        manager = Manager(pg=pg, min_replica_size=2, use_async_quorum=False,
+                          load_state_dict=lambda sd: (model.load_state_dict(sd["model"]), inner.load_state_dict(sd["inner"])),
+                          state_dict=lambda: {"model": model.state_dict(), "inner": inner.state_dict()},
+                          replica_id=f"srep_{rid}", store_addr="127.0.0.1", store_port=store.port, rank=0, world_size=1,
+                          lighthouse_addr=lh_addr, timeout=timedelta(seconds=10), quorum_timeout=timedelta(seconds=30))
+        try:
+            gen = torch.Generator().manual_seed(5)
+            with DiLoCo(manager, [f1, f2], inner, outers, sync_every=4, backup_device=torch.device("cpu"), pin_memory=False,
+                        fragment_sync_delay=1) as d:
+                while manager.current_step() < steps:
+                    if attempt == 0 and crash_at >= 0 and manager.current_step() == crash_at:
+                        raise _Crash()
+                    inner.zero_grad()
+                    model(torch.rand(4, 3, generator=gen)).mean().backward()
+                    inner.step()
+                out[rid] = {"step": manager.current_step(),
+                            "original": [{n: t.clone() for n, t in f.original_parameters.items()} for f in d._fragments],
+                            "outer": [copy.deepcopy(o.state_dict()) for o in outers]}
+            return
+        except _Crash:
+            continue
+        finally:
+            manager.shutdown(wait=False)
+            pg.shutdown()
+
+
+def test_integration_streaming_diloco_recovery_after_crash():
+    """Replica 1 dies mid-run (between fragment syncs) and restarts with fresh weights: it must heal BOTH fragments'
+    backup weights and outer optimizers from replica 0 and finish with identical global state
+    (reference: local_sgd_integ_test 'streaming recovery')."""
+    lh = LighthouseServer(bind="[::]:0", min_replicas=2, join_timeout_ms=300, heartbeat_timeout_ms=1000)
+    out: Dict[int, Any] = {}
+    attempts: Dict[int, int] = {}
+    steps = 6
+    try:
+        with ThreadPoolExecutor(max_workers=2) as ex:
+            futs = [ex.submit(_streaming_replica, lh.address(), 0, steps, -1, out, attempts),
+                    ex.submit(_streaming_replica, lh.address(), 1, steps, 3, out, attempts)]
+            for f in futs:
+                f.result(timeout=180)
+    finally:
+        lh.shutdown()
+    assert attempts == {0: 1, 1: 2}
+    assert out[0]["step"] == out[1]["step"] == steps
+    for frag in range(2):
+        for n in out[0]["original"][frag]:
+            torch.testing.assert_close(out[0]["original"][frag][n], out[1]["original"][frag][n])
+        s0, s1 = out[0]["outer"][frag]["state"], out[1]["outer"][frag]["state"]
+        assert set(s0) == set(s1) and len(s0) > 0
+        for k in s0:
+            torch.testing.assert_close(s0[k]["momentum_buffer"], s1[k]["momentum_buffer"])
