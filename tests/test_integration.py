@@ -164,12 +164,13 @@ class Runner:
         transport = None
         if self.transport == "pg":
             transport = PGTransport(pg, timedelta(seconds=10), torch.device("cpu"))
-        manager = Manager(
+        kwargs: Dict[str, Any] = dict(
             pg=pg, min_replica_size=2, load_state_dict=load_state, state_dict=state, replica_id=str(self.replica_id),
             store_addr="127.0.0.1", store_port=store_port, rank=rank, world_size=self.world_size,
             lighthouse_addr=self.lighthouse_address, use_async_quorum=self.use_async_quorum, init_sync=self.init_sync,
-            timeout=timedelta(seconds=10), quorum_timeout=timedelta(seconds=20), checkpoint_transport=transport,
-            **self.manager_kwargs)
+            timeout=timedelta(seconds=10), quorum_timeout=timedelta(seconds=20), checkpoint_transport=transport)
+        kwargs.update(self.manager_kwargs)
+        manager = Manager(**kwargs)
         stack = ExitStack()
         stack.callback(lambda: manager.shutdown(wait=False))
         stack.callback(pg.shutdown)
@@ -280,6 +281,19 @@ def test_multi_rank_replica_groups(lighthouse):
     res = _run([Runner(i, lighthouse.address(), inj, world_size=2, total_steps=3) for i in range(2)])
     assert all(len(g) == 2 for g in res)
     # each group rank is its own "shard": rank r must match rank r of every other replica group
+    for r in range(2):
+        _assert_equal_state([[g[r]] for g in res])
+
+
+def test_multi_rank_group_recovers_after_one_rank_crashes(lighthouse):
+    """world_size=2 inside each group; rank 0 of one group crashes at step 2. Its sibling rank is stuck in the group barrier
+    until its quorum deadline, the whole group restarts (torchelastic semantics), heals rank-for-rank from the healthy group
+    and both groups finish with identical per-rank state (reference: manager_integ_test multi-rank recovery)."""
+    inj = EventInjector().fail_at(0, 2)
+    short = {"quorum_timeout": timedelta(seconds=4), "timeout": timedelta(seconds=4)}
+    res = _run([Runner(i, lighthouse.address(), inj, world_size=2, total_steps=5, manager_kwargs=short, attempts=4) for i in range(2)])
+    assert inj.count[EventType.FAILURE] == 1
+    assert all(len(g) == 2 and all(r["step"] == 5 for r in g) for g in res)
     for r in range(2):
         _assert_equal_state([[g[r]] for g in res])
 
