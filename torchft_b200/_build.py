@@ -67,6 +67,7 @@ def _run(cmd: List[str]) -> None:
 
 def build_kernels(force: bool = False, verbose: bool = False) -> Path:
     """Compile torchft_b200/_K*.so for sm_100a."""
+
     kdir = CSRC / "kernels"
     cus = sorted(kdir.glob("*.cu"))
     hdrs = sorted(kdir.glob("*.h")) + sorted(kdir.glob("*.cuh"))
@@ -105,6 +106,7 @@ def build_kernels(force: bool = False, verbose: bool = False) -> Path:
 
 def build_control(force: bool = False) -> Path:
     """Compile torchft_b200/_C*.so (C++17 control plane)."""
+
     cdir = CSRC / "control"
     ccs = sorted(cdir.glob("*.cc"))
     hdrs = sorted(cdir.glob("*.h"))
@@ -131,6 +133,7 @@ def build_control(force: bool = False) -> Path:
 
 def build_lighthouse_binary(force: bool = False) -> Path:
     """Standalone `torchft_b200_lighthouse` executable (no Python needed)."""
+
     cdir = CSRC / "control"
     out = ROOT.parent / "bin" / "torchft_b200_lighthouse"
     srcs = [p for p in sorted(cdir.glob("*.cc")) if p.name != "bindings.cc"] + [cdir / "main" / "lighthouse_main.cpp"]
@@ -152,6 +155,7 @@ def build_selftest(force: bool = False, sanitize: str = "") -> Path:
 
     ``sanitize="thread"`` / ``"address"`` builds the same tests under ThreadSanitizer / AddressSanitizer+UBSan
     (bin/torchft_b200_selftest_tsan / _asan) — the race and memory checks of the control plane."""
+
     cdir = CSRC / "control"
     suffix = {"": "", "thread": "_tsan", "address": "_asan"}[sanitize]
     out = ROOT.parent / "bin" / f"torchft_b200_selftest{suffix}"

@@ -23,6 +23,7 @@ def any_nan(tensors: Iterable[torch.Tensor]) -> bool:
 def gen_views(t: torch.Tensor) -> List[Shape]:
     """Every ``(m, n)`` with ``m * n == t.numel()`` and ``m < numel`` (``(1, n)`` only for even sizes,
     matching the reference's enumeration so test matrices line up)."""
+
     size = t.numel()
     first = 1 if size % 2 == 0 else 2
     return [(m, size // m) for m in range(first, size) if size % m == 0]
@@ -30,5 +31,6 @@ def gen_views(t: torch.Tensor) -> List[Shape]:
 
 def gen_splits(t: torch.Tensor, split_size: int) -> List[List[Shape]]:
     """Cartesian product of :func:`gen_views` over the ``split_size`` chunks of ``t``."""
+
     per_chunk: Sequence[List[Shape]] = [gen_views(c) for c in torch.split(t, split_size)]
     return [list(combo) for combo in itertools.product(*per_chunk)]

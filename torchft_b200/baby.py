@@ -124,6 +124,7 @@ def _unflatten(obj: Any) -> Any:
 def _child_main(pg_factory: Callable[[timedelta], ProcessGroup], store_addr: str, cfg: Tuple[Any, ...],
                 timeout_s: float, device: int, req: Any, resp: Any) -> None:
     """Serial command loop of the subprocess."""
+
     try:
         if device >= 0 and torch.cuda.is_available():
             torch.cuda.set_device(device)

@@ -16,6 +16,7 @@ def local_lighthouse(min_replicas: int = 1, join_timeout_ms: int = 100) -> Any:
 
 def loopback(addr: str) -> str:
     """``http://<hostname>:port`` -> ``http://127.0.0.1:port`` (container hostnames may not resolve)."""
+
     host = addr.split("//")[1].rsplit(":", 1)[0]
     return addr.replace(host, "127.0.0.1")
 

@@ -19,6 +19,9 @@ from typing import Generator
 
 
 class RWLock:
+    """Reader-writer lock with timeouts (reference: checkpointing/_rwlock.py:46-136): many readers or one writer;
+    ``r_lock()`` / ``w_lock()`` are context managers, acquisition raises ``TimeoutError`` after ``timeout`` seconds."""
+
     def __init__(self, timeout: float = -1) -> None:
         self.timeout = timeout
         self._cv = threading.Condition(threading.Lock())

@@ -56,6 +56,15 @@ def _to_host(tree: Any) -> Any:
 
 
 class DurableCheckpointer:
+    """Periodic on-disk checkpoints of ``{user state, manager.state_dict()}`` written by ONE replica (see the module docstring).
+
+    Args:
+        manager: the job's :class:`~torchft_b200.Manager` (``current_step``, ``participating_rank``, ``state_dict``).
+        state_dict / load_state_dict: the same hooks the Manager uses for live healing.
+        directory: shared (or per-node) directory; files are ``step_<N>.rank_<group_rank>.pt``.
+        every_n_steps: checkpoint cadence in committed steps; keep: how many files to retain per group rank.
+    """
+
     def __init__(self, manager: Any, state_dict: Callable[[], Any], load_state_dict: Callable[[Any], None], directory: str,
                  every_n_steps: int = 100, keep: int = 2, group_rank: Optional[int] = None) -> None:
         if every_n_steps < 1 or keep < 1:

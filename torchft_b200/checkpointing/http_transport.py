@@ -38,6 +38,7 @@ logger = logging.getLogger(__name__)
 def _advertise_host() -> str:
     """Hostname peers should dial; falls back to loopback when the hostname does not resolve
     (common in containers) -- on-node transports only ever talk to the same host anyway."""
+
     h = socket.gethostname()
     try:
         socket.getaddrinfo(h, None)
@@ -73,6 +74,13 @@ def _to_cpu(obj: Any, pin: bool) -> Any:
 
 
 class HTTPTransport(CheckpointTransport[T], Generic[T]):
+    """Heal over HTTP (the reference's default transport, checkpointing/http_transport.py:38-298).
+
+    ``send_checkpoint`` stages the state on the host and releases a write lock; GET ``/checkpoint/<step>/full``
+    (or ``/metadata`` + ``/<chunk>`` when ``num_chunks > 0``, fetched in parallel) streams it socket-to-tensor;
+    a request for another step gets 400; ``disallow_checkpoint`` re-takes the lock before the optimizer mutates state.
+    """
+
     def __init__(self, timeout: timedelta, num_chunks: int = 0) -> None:
         self._timeout = timeout
         self._num_chunks = num_chunks

@@ -46,6 +46,7 @@ logger = logging.getLogger(__name__)
 def _advertise_host() -> str:
     """Hostname peers should dial; falls back to loopback when the hostname does not resolve
     (common in containers) -- on-node transports only ever talk to the same host anyway."""
+
     h = socket.gethostname()
     try:
         socket.getaddrinfo(h, None)
@@ -63,6 +64,7 @@ def device_copy(entries: Sequence[Tuple[int, int, int]], stream: Optional[torch.
 
     Either side may be a mapped peer pointer; the kernel issues the NVLink loads.
     """
+
     K = _native.load()
     rows, chunk0 = [], 0
     for src, dst, n in entries:

@@ -19,6 +19,9 @@ T = TypeVar("T")
 
 
 class CheckpointTransport(Generic[T], ABC):
+    """Interface of a live-heal transport (reference: checkpointing/transport.py:14-68): the source calls
+    ``send_checkpoint`` / ``disallow_checkpoint``, the healing replica ``recv_checkpoint`` with the source's ``metadata()``."""
+
     @abstractmethod
     def metadata(self) -> str:
         """Opaque string a remote transport needs to fetch from this one (e.g. a URL)."""

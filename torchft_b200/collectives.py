@@ -47,6 +47,7 @@ class _StreamWork(Work):
 
 def get_padded_sizes(tensors: List[torch.Tensor], world_size: int) -> List[torch.Size]:
     """Shapes with dim 0 rounded up to a multiple of ``world_size`` (reference: collectives.py:51-75)."""
+
     out = []
     for t in tensors:
         s = list(t.shape) if t.dim() > 0 else [1]
@@ -57,6 +58,7 @@ def get_padded_sizes(tensors: List[torch.Tensor], world_size: int) -> List[torch
 
 def allocate_reduce_scatter_output(tensors: List[torch.Tensor], world_size: int) -> Tuple[torch.Tensor, List[torch.Size]]:
     """One flat output buffer holding this rank's 1/world_size row-slice of every (padded) tensor."""
+
     padded = get_padded_sizes(tensors, world_size)
     dt, dev = tensors[0].dtype, tensors[0].device
     for t in tensors:
@@ -139,6 +141,7 @@ def allreduce_quantized(tensors: List[torch.Tensor], opts: AllreduceOptions | Re
     all-gather -> dequantize, all enqueued on ``sync_stream`` (a side stream by default).
     Expected mean relative error <= 0.04 (reference tolerance, collectives_test.py:186).
     """
+
     op = _op_of(opts)
     _check(tensors, op)
     world = process_group.size()
@@ -185,6 +188,7 @@ def reduce_scatter_quantized(output: torch.Tensor, inputs: List[torch.Tensor], o
     """fp8 reduce-scatter: ``output`` receives this rank's row-slice of every (row-padded) input,
     concatenated (layout of :func:`allocate_reduce_scatter_output`): quantize -> all-to-all ->
     fp32 reduce -> dequantize own slice. No all-gather."""
+
     op = _op_of(opts)
     _check(inputs, op)
     world = process_group.size()

@@ -62,6 +62,7 @@ def lighthouse_status(addr: str, timeout: timedelta = timedelta(seconds=5)) -> D
 def wait_for_lighthouse(addr: str, timeout: timedelta = timedelta(seconds=60), poll_s: float = 0.2) -> Dict[str, Any]:
     """Block until the Lighthouse at ``addr`` answers (launch scripts start it next to the trainers);
     returns its first status. Raises ``TimeoutError``."""
+
     deadline = time.monotonic() + timeout.total_seconds()
     last: Exception = TimeoutError("not tried")
     while time.monotonic() < deadline:

@@ -32,6 +32,8 @@ PORT_FILE_ENV = "TORCHFT_FAILURE_PORT_FILE"
 
 
 class Failure(enum.Enum):
+    """Injectable failure kinds (reference: examples/monarch/utils/failure.py:24-30, plus ``STALL_PEER``)."""
+
     SEGFAULT = "segfault"      # SIGSEGV in native code
     KILL_PROC = "kill_proc"    # immediate exit(1), no cleanup
     COMMS = "comms"            # abort the fault-tolerant process group under the trainer
@@ -40,6 +42,8 @@ class Failure(enum.Enum):
 
 
 class FailureInjector:
+    """In-process fault injector: ``inject(kind)`` directly, or ``start()`` to accept one-word commands on a loopback port."""
+
     def __init__(self, manager: Any = None, pg: Any = None, deadlock_secs: int = 70) -> None:
         self._manager = manager
         self._pg = pg if pg is not None else getattr(manager, "_pg", None)

@@ -205,6 +205,7 @@ def future_timeout(fut: "Future[T]", timeout: timedelta) -> "Future[T]":
 
 def future_wait(fut: "Future[T]", timeout: timedelta) -> T:
     """Block for ``fut`` at most ``timeout``; raises ``TimeoutError`` (the future itself is untouched)."""
+
     ev = threading.Event()
     fut.add_done_callback(lambda _f: ev.set())
     if not ev.wait(timeout.total_seconds()):

@@ -24,6 +24,8 @@ from typing import Dict, List, Optional
 
 @dataclass
 class Role:
+    """One launchable unit (a torchrun invocation for one replica group) of a job spec; mirrors ``torchx.specs.Role``."""
+
     name: str
     entrypoint: str
     args: List[str]
@@ -36,6 +38,7 @@ def hsdp(*script_args: str, replicas: int = 2, workers_per_replica: int = 1, max
          script: str = "train_ddp.py", env: Optional[Dict[str, str]] = None, lighthouse: Optional[str] = None,
          base_port: int = 29600, gpus_per_node: Optional[int] = None) -> List[Role]:
     """Job spec for fault-tolerant HSDP: ``replicas`` replica groups x ``workers_per_replica`` ranks."""
+
     env = dict(env or {})
     lighthouse = lighthouse or os.environ.get("TORCHFT_LIGHTHOUSE", "http://127.0.0.1:29510")
     roles = []
@@ -58,6 +61,7 @@ def hsdp(*script_args: str, replicas: int = 2, workers_per_replica: int = 1, max
 def launch_local(roles: List[Role], poll_s: float = 1.0, relaunch: bool = False) -> int:
     """Run every role as a local subprocess; with ``relaunch`` dead groups are restarted (a poor
     man's scheduler, like the reference's slurm runner loop). Returns the worst exit code."""
+
     procs: Dict[str, subprocess.Popen] = {}
 
     def start(r: Role) -> None:

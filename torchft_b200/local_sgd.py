@@ -53,6 +53,7 @@ def _is_dtensor(t: Any) -> bool:
 
 def extract_local_tensor(t: torch.Tensor) -> torch.Tensor:
     """Detached clone of ``t`` (of its local shard when ``t`` is a DTensor)."""
+
     src = t.to_local() if _is_dtensor(t) else t
     out = src.detach().clone()
     out.grad = None

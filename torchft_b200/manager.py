@@ -73,6 +73,7 @@ def get_timeout(timeout_sec_env: Optional[str], default_timeout: timedelta) -> t
 
 def extract_trailing_digits(s: str) -> int:
     """``"replica_12"`` -> 12; 0 when the string does not end in digits."""
+
     digits = ""
     for ch in reversed(s):
         if not ch.isdigit():
@@ -94,6 +95,8 @@ class WorldSizeMode(Enum):
 
 
 class ExceptionWithTraceback(Exception):
+    """Wraps the first error reported in a step together with its formatted traceback (reference: manager.py:141-145)."""
+
     def __init__(self, e: Exception) -> None:
         self.original_exception = e
         self.stack_trace = traceback.format_exc()

@@ -31,6 +31,8 @@ from torchft_b200.ops import fused
 
 @dataclass
 class LlamaConfig:
+    """Architecture hyper-parameters (defaults = Llama-3-8B) plus the activation-checkpoint policy and the loss chunk size."""
+
     dim: int = 4096
     n_layers: int = 32
     n_heads: int = 32
@@ -72,6 +74,9 @@ CONFIGS: Dict[str, LlamaConfig] = {
 
 
 class Block(nn.Module):
+    """Pre-norm transformer block on the fused kernels: norm+QKV GEMM, RoPE+split, SDPA, output GEMM with the residual in
+    its epilogue, norm+gate/up GEMM, SwiGLU+down GEMM with the residual in its epilogue."""
+
     def __init__(self, cfg: LlamaConfig, device=None, dtype=torch.bfloat16) -> None:
         super().__init__()
         d, hd = cfg.dim, cfg.head_dim
@@ -102,6 +107,9 @@ class Block(nn.Module):
 
 
 class Llama(nn.Module):
+    """Decoder-only Llama-3 style model; ``forward(tokens, targets)`` returns the mean next-token loss through the chunked
+    linear-cross-entropy (no fp32 logits), ``forward(tokens)`` returns logits."""
+
     def __init__(self, cfg: LlamaConfig, device=None, dtype=torch.bfloat16) -> None:
         super().__init__()
         self.cfg = cfg

@@ -28,6 +28,7 @@ def _rope(x: torch.Tensor, theta: float) -> torch.Tensor:
 
 def reference_loss(model, tokens: torch.Tensor, targets: torch.Tensor) -> Tuple[float, Dict[str, torch.Tensor]]:
     """Returns (loss, {param_name: fp32 grad}) computed with eager fp32 PyTorch."""
+
     cfg = model.cfg
     P = {n: p.detach().float().requires_grad_() for n, p in model.named_parameters()}
     B, S = tokens.shape

@@ -20,6 +20,7 @@ def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor) -> torch.Tensor
     view; autograd then adopts it as ``W.grad`` without a copy. This removes the per-step
     zero-fill of the gradient buffer and the read-modify-write accumulation pass (~64 GB of HBM
     traffic per step for an 8B model): the wgrad epilogue IS the bucket write."""
+
     slot = getattr(W, "_flat_grad", None)
     if slot is not None and W.grad is None and slot.dtype == dy2.dtype:
         return torch.mm(dy2.t(), x2, out=slot.view(W.shape))
@@ -104,6 +105,7 @@ def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
 
 def rope_table(seq_len: int, head_dim: int, theta: float, device: torch.device) -> torch.Tensor:
     """(cos, sin) table ``[seq_len, head_dim/2, 2]`` fp32 for interleaved-pair RoPE."""
+
     inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=device) / head_dim))
     ang = torch.outer(torch.arange(seq_len, dtype=torch.float32, device=device), inv)
     return torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous()
@@ -212,6 +214,7 @@ def linear_cross_entropy(h: torch.Tensor, weight: torch.Tensor, target: torch.Te
 
 def cross_entropy_inplace(logits: torch.Tensor, target: torch.Tensor, grad_scale: float = 1.0, ignore_index: int = -100) -> torch.Tensor:
     """Per-row CE losses; overwrites ``logits`` (bf16, [rows, V]) with grad_scale * dlogits."""
+
     K = _native.load()
     assert logits.dim() == 2 and logits.stride(1) == 1
     losses = torch.empty(logits.shape[0], dtype=torch.float32, device=logits.device)

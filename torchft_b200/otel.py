@@ -138,6 +138,7 @@ def _setup_otel(name: str) -> None:
 
 def setup_logger(name: str) -> None:
     """Attach the configured sinks to logger ``name`` (idempotent)."""
+
     logger = logging.getLogger(name)
     path = os.environ.get(EVENTS_JSONL_ENV)
     if path and name not in _JSONL:

@@ -88,6 +88,14 @@ class StreamWork(Work):
 
 
 class ProcessGroupB200(ProcessGroup):
+    """Fault-tolerant process group over NVLink peer memory (see the module docstring).
+
+    Args:
+        timeout: spin budget of every in-kernel wait and of store operations.
+        staging_bytes: size of the staging buffer used for tensors outside symmetric memory (default 64 MB).
+        device: CUDA device of this rank (default: current device).
+    """
+
     def __init__(self, timeout: timedelta = timedelta(seconds=60), staging_bytes: Optional[int] = None,
                  device: Optional[torch.device] = None) -> None:
         super().__init__(0, 1)

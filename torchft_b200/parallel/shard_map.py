@@ -31,12 +31,16 @@ def _weight(shard: int, replica_id: str) -> int:
 
 @dataclass(frozen=True)
 class Transition:
+    """Result of :meth:`ShardMap.plan_transition`: copies to perform, shards nobody survived with, untouched pairs."""
+
     copies: Tuple[Tuple[int, str, str], ...]  # (shard, source replica id, destination replica id)
     lost: Tuple[int, ...]                     # shards none of whose previous owners is still alive
     kept: int                                 # (shard, owner) pairs that did not move
 
 
 class ShardMap:
+    """``num_shards`` virtual shards, each held by ``replication`` replicas chosen by rendezvous hashing over replica ids."""
+
     def __init__(self, num_shards: int = 256, replication: int = 2) -> None:
         if num_shards < 1 or replication < 1:
             raise ValueError("num_shards and replication must be >= 1")

@@ -50,6 +50,9 @@ class _Server(ThreadingHTTPServer):
 
 
 class ParameterServer(ABC):
+    """Prototype parameter server (reference: parameter_server.py:30-194): an HTTP endpoint hands out sessions, each session is a
+    fresh 2-rank reconfigurable process group (server rank 0, client rank 1); subclasses implement ``new_process_group`` and ``forward``."""
+
     def __init__(self, port: int, store_port: int = 0) -> None:
         """
         Args:

@@ -65,6 +65,7 @@ def create_store_client(store_addr: str, timeout: timedelta) -> Store:
 
 def trigger_nccl_fr_trace_through_pipe(rank: int) -> bool:
     """Ask the NCCL flight recorder to dump through its named pipe (reference :92-106)."""
+
     prefix = os.environ.get(TORCH_NCCL_DEBUG_INFO_PIPE_FILE_ENV_VAR, "")
     if not prefix:
         logger.info("[rank %d] flight-recorder pipe not enabled", rank)

@@ -39,6 +39,7 @@ def q8_bytes(numel: int, world_size: int) -> int:
 
 def quantize_q8(x: torch.Tensor, world_size: int = 1, subtract: torch.Tensor | None = None) -> torch.Tensor:
     """Quantise ``x`` (optionally ``x - subtract``) into a fresh uint8 Q8G buffer."""
+
     K = _native.load()
     _check(x)
     buf = torch.empty(K.q8_buffer_bytes(x.numel(), world_size), dtype=torch.uint8, device=x.device)
@@ -67,6 +68,7 @@ def _layout(inputs: Sequence[torch.Tensor], world_size: int) -> Tuple[List[int],
 
 def fused_quantize_into_fp8(inputs: List[torch.Tensor], world_size: int) -> torch.Tensor:
     """Quantise a list of tensors into one uint8 buffer (reference: quantization.py:531-588)."""
+
     K = _native.load()
     offs, total = _layout(inputs, world_size)
     buf = torch.empty(total, dtype=torch.uint8, device=inputs[0].device)
@@ -80,6 +82,7 @@ def fused_quantize_into_fp8(inputs: List[torch.Tensor], world_size: int) -> torc
 
 def fused_dequantize_from_fp8(inputs: List[torch.Tensor], quantized: torch.Tensor, world_size: int) -> None:
     """Dequantise ``quantized`` back into ``inputs`` in place (reference: quantization.py:591-635)."""
+
     K = _native.load()
     offs, total = _layout(inputs, world_size)
     assert quantized.numel() >= total
@@ -103,6 +106,7 @@ def fused_reduce_fp8(inputs: List[torch.Tensor], all_buffers: List[torch.Tensor]
     written into ``all_buffers[rank]`` (reference: quantization.py:638-686, where
     the buffers are the rows of the all-to-all output).
     """
+
     K = _native.load()
     if reduce_op not in (ReduceOp.SUM, ReduceOp.AVG):
         raise NotImplementedError(f"unsupported reduce op {reduce_op}")
@@ -120,6 +124,7 @@ def fused_reduce_fp8(inputs: List[torch.Tensor], all_buffers: List[torch.Tensor]
 def rank_slice_views(inputs: Sequence[torch.Tensor], buf: torch.Tensor, world_size: int, rank: int) -> List[torch.Tensor]:
     """uint8 views of the parts of a :func:`fused_quantize_into_fp8` buffer that rank ``rank`` owns:
     per tensor, its run of fp32 scales and its run of 512-byte payload groups."""
+
     K = _native.load()
     offs, _ = _layout(inputs, world_size)
     views = []

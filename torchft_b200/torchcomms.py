@@ -42,6 +42,7 @@ _HANDLE_KEY = "torchcomms_init_handle/{}"
 
 def new_torchcomm(backend: str, device: torch.device, name: str = "torchft_b200", **kwargs: Any) -> Any:
     """Create a reconfigurable ``torchcomms.TorchComm`` (raises ImportError when the package is absent)."""
+
     try:
         import torchcomms  # type: ignore[import-not-found]
     except ImportError as e:  # pragma: no cover - not in this image

@@ -25,6 +25,7 @@ def hsdp(*script_args: str, replicas: int = 2, workers_per_replica: int = 1, max
     Args mirror the reference component; ``h`` is a torchx named resource, otherwise
     ``cpu/gpu/memMB`` are used. Raises ``ImportError`` when torchx is not installed.
     """
+
     try:
         from torchx import specs  # type: ignore[import-not-found]
     except ImportError as e:
