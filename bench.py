@@ -119,6 +119,8 @@ def main() -> None:
     args = ap.parse_args()
 
     if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:  # under torchrun only rank 0 reports
+            return
         print(json.dumps({
             "impl": "reference",
             "unavailable": "reference build backend (maturin) and its toolchain (cargo/rustc, protoc) are not "
