@@ -308,3 +308,25 @@ def test_punisher_kills_a_replica_through_the_lighthouse(tmp_path):
         if p.poll() is None:
             p.kill()
         lh.shutdown()
+
+
+def test_launch_local_relaunches_failed_roles_until_they_succeed(tmp_path):
+    """launcher.launch_local(relaunch=True): a role that exits non-zero is started again (poor man's scheduler)."""
+    from torchft_b200.launcher import Role, launch_local
+
+    marker = tmp_path / "attempts"
+    script = tmp_path / "flaky.py"
+    script.write_text(
+        "import os, sys\n"
+        f"p = {str(marker)!r}\n"
+        "n = int(open(p).read()) if os.path.exists(p) else 0\n"
+        "open(p, 'w').write(str(n + 1))\n"
+        "sys.exit(0 if n >= 2 else 3)\n")
+    ok = tmp_path / "ok.py"
+    ok.write_text("print('fine')\n")
+    roles = [Role(name="flaky", entrypoint=sys.executable, args=[str(script)]),
+             Role(name="steady", entrypoint=sys.executable, args=[str(ok)], env={"X": "1"})]
+    assert launch_local(roles, poll_s=0.1, relaunch=True) == 0
+    assert marker.read_text() == "3"  # failed twice, succeeded on the third launch
+    marker.unlink()
+    assert launch_local(roles[:1], poll_s=0.1, relaunch=False) == 3  # without relaunch the exit code is reported
