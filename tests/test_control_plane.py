@@ -550,3 +550,40 @@ def test_server_survives_malformed_traffic(lighthouse):
     c.heartbeat("after_fuzz", timedelta(seconds=1))
     status = urllib.request.urlopen(f"http://127.0.0.1:{port}/status.json").read()
     assert b"after_fuzz" in status
+
+
+@pytest.mark.parametrize("how", ["python_module", "standalone_binary"])
+def test_lighthouse_command_line(how):
+    """`python -m torchft_b200.lighthouse` and the stand-alone binary take the reference's flags (+ --quorum_id_base),
+    serve RPC + dashboard on one port, and stop on SIGINT/SIGTERM."""
+    import signal
+    import socket
+    import subprocess
+    import sys
+
+    from torchft_b200 import _build
+    from torchft_b200.coordination import wait_for_lighthouse
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    flags = ["--bind", f"127.0.0.1:{port}", "--min_replicas", "3", "--join_timeout_ms", "250", "--quorum_tick_ms", "20",
+             "--heartbeat_timeout_ms", "1500", "--quorum_id_base", "auto"]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torchft_b200.lighthouse"] if how == "python_module" else [str(_build.build_lighthouse_binary())]
+    p = subprocess.Popen(cmd + flags, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        st = wait_for_lighthouse(f"http://127.0.0.1:{port}", timedelta(seconds=60))
+        assert st["min_replicas"] == 3 and st["heartbeat_timeout_ms"] == 1500 and st["quorum_id"] > 10 ** 6  # clock-based base
+        c = _C.LighthouseClient(f"http://127.0.0.1:{port}", timedelta(seconds=5))
+        c.heartbeat("cli_probe", timedelta(seconds=2))
+        with pytest.raises(TimeoutError):
+            c.quorum("cli_probe", timedelta(milliseconds=300))  # 1 of min_replicas=3
+        p.send_signal(signal.SIGINT if how == "python_module" else signal.SIGTERM)
+        assert p.wait(20) is not None
+    finally:
+        if p.poll() is None:
+            p.kill()
+    # a missing required flag is a usage error, not a hang
+    r = subprocess.run(cmd + ["--bind", "127.0.0.1:0"], cwd=root, capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "min_replicas" in (r.stdout + r.stderr)
