@@ -432,6 +432,8 @@ def test_native_selftest_under_sanitizers(sanitize, needle):
                UBSAN_OPTIONS="print_stacktrace=1")
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=env)
     out = r.stdout + r.stderr
+    if "selftest:" not in r.stdout and ("unexpected memory mapping" in out or "Shadow memory" in out or "ReserveShadowMemoryRange" in out):
+        pytest.skip(f"{sanitize} sanitizer runtime cannot start in this environment (ASLR / address-space layout)")
     assert "0 failed" in r.stdout, out[-3000:]
     assert needle not in out and "runtime error" not in out, out[-4000:]
     assert r.returncode == 0
