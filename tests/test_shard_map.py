@@ -1,9 +1,13 @@
 """Property tests (hypothesis) of the rendezvous-hashed ownership map for replicated virtual shards."""
 
-from hypothesis import given, settings
-from hypothesis import strategies as st
+import pytest
 
-from torchft_b200.parallel.shard_map import ShardMap
+pytest.importorskip("hypothesis")
+
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+from torchft_b200.parallel.shard_map import ShardMap  # noqa: E402
 
 ids = st.lists(st.integers(0, 40).map(lambda i: f"replica_{i}"), min_size=1, max_size=12, unique=True)
 
