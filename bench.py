@@ -6,19 +6,27 @@
 
 Metric (BASELINE.json): whole-job tokens/s of Llama-3-8B bf16 training with the
 per-step fault-tolerance protocol ON (Lighthouse quorum + cross-replica gradient
-all-reduce + should_commit + AdamW), N replica groups of one GPU each (HSDP with
+reduction + commit decision + AdamW), N replica groups of one GPU each (HSDP with
 shard degree 1; weak scaling: per-GPU batch fixed), synthetic tokens, random-init
-weights. Every step runs: start_quorum (async), forward, backward with per-bucket
-fused P2P all-reduce overlapped, should_commit RPC, single-launch AdamW.
+weights. Every native step runs FT-ZeRO-1 (torchft_b200/parallel/zero1.py): start_quorum
+(async), forward, backward with one fused reduce-scatter kernel per transformer block
+overlapped, ONE device-side commit-verdict kernel (no host sync, no RPC), gated AdamW on
+the held slices fused with the all-gather of the new bf16 weights under the next forward.
 
 `value`   : device-timed (CUDA events), inputs resident on the GPU, max over ranks.
-`e2e`     : same loop through the public trainer API, wall-clock, including per step
-            the pinned-host -> device copy of tokens/targets and a device -> host
-            read of the loss.
+`e2e`     : same loop through the public trainer API (`FaultTolerantTrainer.step_async`),
+            wall-clock, including per step the pinned-host -> device copy of tokens/targets
+            and a device -> host read of the loss (pinned, read back one step late so the
+            host never drains the GPU queue).
 `--impl reference` : the unmodified reference cannot be installed offline (its build
             backend maturin + cargo/protoc are absent) -> prints {"unavailable": ...}.
-`--impl nccl`      : same model/loop with the reference-EQUIVALENT data plane (stock
-            ProcessGroupNCCL re-created per quorum, SUM then /N), for our own A/B.
+`--impl nccl`      : same model/loop with the reference-EQUIVALENT structure: stock
+            ProcessGroupNCCL re-created per quorum, all-reduce SUM then /N, host-synchronous
+            should_commit RPC, full AdamW on every replica (reference manager.py:466-478,
+            884-903, optim.py:52-55).
+The native arm also runs the nccl arm afterwards IN THE SAME PROCESS (the reference publishes
+no numbers, BASELINE.md) and reports `vs_baseline` = native / nccl-equivalent;
+`--no-baseline-arm` skips it.
 """
 
 from __future__ import annotations
@@ -104,6 +112,113 @@ class ClockSampler:
         return out
 
 
+def run_arm(impl: str, args, rank: int, world: int, local: int, lh_addr: str) -> dict:
+    """Build a trainer for ``impl``, warm up, time K steps on the device and K steps end to end, tear down."""
+    import gc
+
+    import torch
+    import torch.distributed as dist
+
+    from torchft_b200.ops import _native
+    from torchft_b200.parallel.trainer import FaultTolerantTrainer
+
+    dev = torch.device("cuda", local)
+    backend = "b200" if impl == "native" else "nccl"
+
+    def build(ac):
+        return FaultTolerantTrainer(args.model, lh_addr, replica_id=f"{impl}_{rank}", min_replica_size=world,
+                                    backend=backend, bucket_mb=args.bucket_mb, should_quantize=args.quantize,
+                                    activation_checkpoint=ac, timeout=timedelta(seconds=120), device=dev,
+                                    replication=args.replication)
+
+    ac = args.ac
+    trainer = build(ac)
+    cfg = trainer.cfg
+    B, S = args.batch, args.seq
+    gen = torch.Generator().manual_seed(1234 + rank)
+    tok_cpu = torch.randint(0, cfg.vocab_size, (B, S), generator=gen).pin_memory()
+    tgt_cpu = torch.randint(0, cfg.vocab_size, (B, S), generator=gen).pin_memory()
+    tok = tok_cpu.to(dev)
+    tgt = tgt_cpu.to(dev)
+
+    def barrier() -> None:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warmup = max(args.warmup, 3)
+    # ---- warm-up (untimed); falls back to full activation checkpointing on OOM ----
+    try:
+        for _ in range(warmup):
+            trainer.step_device(tok, tgt)
+        torch.cuda.synchronize()
+    except torch.OutOfMemoryError:
+        if ac == "full":
+            raise
+        trainer.shutdown()
+        if hasattr(trainer.pg, "comm"):
+            trainer.pg.comm.free_segments()
+        del trainer
+        gc.collect()
+        torch.cuda.empty_cache()
+        ac = "full"
+        trainer = build(ac)
+        for _ in range(warmup):
+            trainer.step_device(tok, tgt)
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    # ---- phase A: device-timed, inputs resident on the GPU ----
+    barrier()
+    launches0 = _native.kernel_launches()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss = trainer.step_device(tok, tgt)
+    trainer.join()  # the last step's optimizer update / weight all-gather (side stream) is inside the timed region
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _native.kernel_launches() - launches0
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    loss_v = float(loss.item())
+    committed = trainer.manager.current_step()
+
+    # ---- phase B: end to end through the public API (H2D inputs + D2H loss every step) ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        trainer.step_async(tok_cpu, tgt_cpu)
+    loss_e2e = trainer.last_loss()  # the last step's loss has reached the host
+    barrier()  # device-wide synchronize: the last update is inside the timed region too
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    committed_total = trainer.manager.current_step()
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    out = {
+        "impl": impl, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "launches": int(launches), "clocks": clocks,
+        "loss": loss_v, "loss_e2e": loss_e2e, "committed": int(committed), "committed_total": int(committed_total),
+        "peak_gib": torch.cuda.max_memory_allocated() / 2**30, "ac": ac or cfg.activation_checkpoint,
+        "warmup": warmup, "cfg": cfg, "h2d": int(tok_cpu.numel() * 8 + tgt_cpu.numel() * 8),
+        "zero1": bool(getattr(trainer, "zero1", False)),
+        "state_gib": (trainer.zopt.state_bytes_held() / 2**30) if getattr(trainer, "zopt", None) is not None else None,
+    }
+    trainer.shutdown()
+    barrier()  # every peer has unmapped our segments
+    if hasattr(trainer.pg, "comm"):
+        trainer.pg.comm.free_segments()
+    del trainer, tok, tgt
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -115,7 +230,10 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=1, help="sequences per GPU per step")
     ap.add_argument("--bucket-mb", type=float, default=512.0)
     ap.add_argument("--quantize", action="store_true")
+    ap.add_argument("--replication", type=int, default=2, help="FT-ZeRO-1: holders per slice of optimizer state")
     ap.add_argument("--ac", default=None, help="activation checkpointing: none|full (default: auto)")
+    ap.add_argument("--no-baseline-arm", action="store_true",
+                    help="native arm only: skip the in-process run of the reference-equivalent NCCL arm")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -137,11 +255,8 @@ def main() -> None:
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
 
     from torchft_b200.coordination import LighthouseServer
-    from torchft_b200.ops import _native
-    from torchft_b200.parallel.trainer import FaultTolerantTrainer
 
     # bootstrap only (publish the lighthouse address, reduce timings): gloo on CPU
     lighthouse = None
@@ -160,128 +275,92 @@ def main() -> None:
     host = lh_addr.split("//")[1].rsplit(":", 1)[0]
     lh_addr = lh_addr.replace(host, "127.0.0.1")
 
-    backend = "b200" if args.impl == "native" else "nccl"
+    res = run_arm(args.impl, args, rank, world, local, lh_addr)
+    base = None
+    if args.impl == "native" and not args.no_baseline_arm:
+        try:
+            base = run_arm("nccl", args, rank, world, local, lh_addr)
+        except Exception as e:  # noqa: BLE001 - the headline must not depend on the comparison arm
+            base = {"error": f"{type(e).__name__}: {e}"}
 
-    def build(ac):
-        return FaultTolerantTrainer(args.model, lh_addr, replica_id=f"replica_{rank}", min_replica_size=world,
-                                    backend=backend, bucket_mb=args.bucket_mb, should_quantize=args.quantize,
-                                    activation_checkpoint=ac, timeout=timedelta(seconds=120), device=dev)
-
-    ac = args.ac
-    trainer = build(ac)
-    cfg = trainer.cfg
+    cfg = res["cfg"]
     B, S = args.batch, args.seq
-    gen = torch.Generator().manual_seed(1234 + rank)
-    tok_cpu = torch.randint(0, cfg.vocab_size, (B, S), generator=gen).pin_memory()
-    tgt_cpu = torch.randint(0, cfg.vocab_size, (B, S), generator=gen).pin_memory()
-    tok = tok_cpu.to(dev)
-    tgt = tgt_cpu.to(dev)
-
-    def barrier() -> None:
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- warm-up (untimed); falls back to full activation checkpointing on OOM ----
-    try:
-        for _ in range(max(args.warmup, 3)):
-            trainer.step_device(tok, tgt)
-        torch.cuda.synchronize()
-    except torch.OutOfMemoryError:
-        if ac == "full":
-            raise
-        trainer.shutdown()
-        del trainer
-        torch.cuda.empty_cache()
-        ac = "full"
-        trainer = build(ac)
-        for _ in range(max(args.warmup, 3)):
-            trainer.step_device(tok, tgt)
-        torch.cuda.synchronize()
-    warmup = max(args.warmup, 3)
-
-    sampler = ClockSampler(local)
-    # ---- phase A: device-timed, inputs resident on the GPU ----
-    barrier()
-    launches0 = _native.kernel_launches()
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        loss = trainer.step_device(tok, tgt)
-    ev1.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = _native.kernel_launches() - launches0
-    dev_ms = ev0.elapsed_time(ev1) / args.steps
-    loss_v = float(loss.item())
-    committed = trainer.manager.current_step()
-
-    # ---- phase B: end to end through the public API (H2D inputs + D2H loss each step) ----
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss_e2e = trainer.step(tok_cpu, tgt_cpu)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
     tokens = B * S * world
-    value = tokens / dev_ms * 1e3
-    e2e_value = tokens / e2e_ms * 1e3
-    peak_gib = torch.cuda.max_memory_allocated() / 2**30
+    value = tokens / res["dev_ms"] * 1e3
+    e2e_value = tokens / res["e2e_ms"] * 1e3
     flops = cfg.flops_per_token(S) * B * S  # per GPU per step
 
     if rank == 0:
+        native = args.impl == "native"
         out = {
             "metric": "tokens/sec (whole job, Llama-3-8B fault-tolerant training step, bf16)",
             "value": round(value, 1),
             "unit": "tokens/s",
             "n_gpus": world,
             "steps": args.steps,
-            "warmup": warmup,
-            "ms_per_step": round(dev_ms, 2),
+            "warmup": res["warmup"],
+            "ms_per_step": round(res["dev_ms"], 2),
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
             "dtype": "bf16",
             "data": "synthetic tokens (uniform random ids), random-init weights",
-            "impl": "torchft_b200" if args.impl == "native" else "nccl-equivalent-baseline (stock ProcessGroupNCCL data plane)",
+            "impl": "torchft_b200" if native else "nccl-equivalent-baseline (stock ProcessGroupNCCL data plane)",
             "config": {
                 "model": args.model,
                 "params_b": round(cfg.num_params() / 1e9, 3),
                 "global_batch": B * world,
                 "seq_len": S,
-                "parallelism": f"ft-hsdp: {world} replica group(s) x 1 GPU (shard degree 1), fault-tolerant DP over NVLink",
-                "optimizer": "AdamW (fp32 master/m/v), applied only after should_commit; one launch per forward stage on a side stream so the next forward overlaps the update" if getattr(trainer, "_opt_stream", None) is not None else "AdamW (fp32 master/m/v), single fused launch after should_commit",
-                "activation_checkpoint": ac or cfg.activation_checkpoint,
-                "grad_allreduce": "fused P2P kernel, zero-copy symmetric buckets, overlapped with backward" if args.impl == "native" else "NCCL allreduce SUM + div",
+                "parallelism": (f"ft-ddp over {world} replica group(s) x 1 GPU (HSDP shard degree 1)"
+                                + (f" + FT-ZeRO-1: optimizer state partitioned over the replicas, k={min(args.replication, world)} holders per slice"
+                                   if res["zero1"] else "")),
+                "optimizer": ("AdamW (fp32 master/m/v) on the held 1/N slices, gated by the device-side commit verdict, fused with the "
+                              "all-gather of the new bf16 weights; one launch per transformer block under the next forward") if res["zero1"]
+                             else "AdamW (fp32 master/m/v), full on every replica, applied only after the host-synchronous should_commit",
+                "activation_checkpoint": res["ac"],
+                "grad_reduction": ("fused reduce-scatter kernel per block over NVLink peer memory (1/N scale, bf16 cast, zero "
+                                   "contribution, buddy push), zero-copy symmetric buffers, overlapped with backward") if res["zero1"]
+                                  else ("fused P2P all-reduce" if native else "NCCL allreduce SUM + div"),
+                "commit": "device-side verdict kernel, host learns lazily (no stream sync, no RPC per step)" if res["zero1"]
+                          else "host stream synchronize + should_commit RPC per step",
                 "quantized_allreduce": bool(args.quantize),
                 "l2_policy": "inputs larger than L2 (16 GB of weights + 16 GB of gradients stream through every step)",
-                "ft_protocol_per_step": "start_quorum(async) + should_commit RPC (C++ control plane, in timed region)",
+                "ft_protocol_per_step": "start_quorum(async, C++ control plane) + commit decision, in the timed region",
             },
             "e2e": {
                 "value": round(e2e_value, 1),
                 "unit": "tokens/s",
-                "ms_per_step": round(e2e_ms, 2),
-                "h2d_bytes_per_step": int(tok_cpu.numel() * 8 + tgt_cpu.numel() * 8),
+                "ms_per_step": round(res["e2e_ms"], 2),
+                "h2d_bytes_per_step": res["h2d"],
                 "d2h_bytes_per_step": 4,
-                "timing": "host wall clock between barriers, max over ranks",
+                "timing": "host wall clock between barriers, max over ranks; loss read back from pinned memory one step late",
             },
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "model_tflops_per_gpu": round(flops / dev_ms / 1e9, 1),
-            "peak_mem_gib": round(peak_gib, 1),
-            "loss": round(loss_v, 4),
-            "steps_committed": int(committed),
+            "gpu_launches": res["launches"],
+            "clocks": res["clocks"],
+            "model_tflops_per_gpu": round(flops / res["dev_ms"] / 1e9, 1),
+            "peak_mem_gib": round(res["peak_gib"], 1),
+            "optimizer_state_gib_held": None if res["state_gib"] is None else round(res["state_gib"], 1),
+            "loss": round(res["loss"], 4),
+            "steps_committed": res["committed"],
+            "steps_committed_incl_e2e": res["committed_total"],
         }
+        if base is not None:
+            if "error" in base:
+                out["baseline_arm"] = base
+            else:
+                bval = tokens / base["dev_ms"] * 1e3
+                out["vs_baseline"] = round(value / bval, 4)
+                out["baseline_arm"] = {
+                    "what": "reference-equivalent arm run in this same process right after the native arm (the reference "
+                            "publishes no number and cannot be installed offline): stock ProcessGroupNCCL, allreduce SUM + /N, "
+                            "host-synchronous should_commit RPC, full AdamW per replica",
+                    "value": round(bval, 1), "ms_per_step": round(base["dev_ms"], 2),
+                    "e2e_value": round(tokens / base["e2e_ms"] * 1e3, 1), "e2e_ms_per_step": round(base["e2e_ms"], 2),
+                    "e2e_ratio": round(base["e2e_ms"] / res["e2e_ms"], 4),
+                    "clocks": base["clocks"], "peak_mem_gib": round(base["peak_gib"], 1), "loss": round(base["loss"], 4),
+                }
         print(json.dumps(out), flush=True)
 
-    trainer.shutdown()
     if world > 1:
         dist.barrier()  # every rank is done with the lighthouse before rank 0 stops it
     if lighthouse is not None:

@@ -23,6 +23,20 @@ void allreduce_nvls_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, 
                            float scale, uint64_t flag, int channel, int contribute, int blocks, int threads,
                            int barrier_mode, cudaStream_t stream);
 
+// zero1.cu -------------------------------------------------------------------
+// FT-ZeRO-1: reduce-scatter (+ buddy push), device-side commit verdict, gated AdamW fused with the
+// all-gather of the new bf16 weights. mc_base != nullptr selects the NVLS (multimem) data path.
+void zero1_reduce_scatter_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, size_t off, size_t nelem,
+                                 float scale, uint64_t flag, int channel, int contribute, int replication,
+                                 int blocks, int threads, int barrier_mode, cudaStream_t stream);
+void zero1_commit_launch(const PeerTable& pt, StatusBlock* st, int* gate, uint64_t flag, uint32_t seq, int channel,
+                         int host_ok, int exchange, cudaStream_t stream);
+void zero1_adamw_allgather_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, const int* gate, size_t poff,
+                                  const void* grad, float* master, float* m, float* v, size_t nelem, float lr,
+                                  float b1, float b2, float eps, float wd, uint64_t flag, int channel,
+                                  int replication, int mode, int blocks, int threads, int barrier_mode,
+                                  cudaStream_t stream);
+
 // quant.cu -------------------------------------------------------------------
 size_t q8_ngroups(size_t nelem, int world);
 size_t q8_buffer_bytes(size_t nelem, int world);

@@ -48,6 +48,11 @@ class Status {
     host_->error_rank = 0;
     host_->error_seq = 0;
   }
+  // Verdict of commit `seq` written by zero1_commit_kernel: -1 = not there (yet), else 0 / 1.
+  int verdict(uint32_t seq) const {
+    const uint32_t v = host_->verdict[seq & (kVerdictRing - 1)];
+    return (v >> 1) == (seq & 0x7fffffffu) ? (int)(v & 1u) : -1;
+  }
   void set_timeout_ms(double ms) { host_->timeout_ns = (uint64_t)(ms * 1e6); }
   double timeout_ms() const { return (double)host_->timeout_ns / 1e6; }
   StatusBlock* dev() const { return dev_; }
@@ -165,6 +170,7 @@ PYBIND11_MODULE(_K, m) {
       .def("aborted", &Status::aborted)
       .def("error", &Status::error)
       .def("clear", &Status::clear)
+      .def("verdict", &Status::verdict)
       .def("set_timeout_ms", &Status::set_timeout_ms)
       .def("timeout_ms", &Status::timeout_ms);
 
@@ -211,6 +217,41 @@ PYBIND11_MODULE(_K, m) {
       py::arg("pt"), py::arg("status"), py::arg("mc_base"), py::arg("off"), py::arg("nelem"), py::arg("dtype"),
       py::arg("scale"), py::arg("flag"), py::arg("channel"), py::arg("contribute"), py::arg("blocks"),
       py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
+
+  m.def(
+      "zero1_reduce_scatter",
+      [](const PeerTableH& pt, const Status& st, uintptr_t mc_base, size_t off, size_t nelem, float scale,
+         uint64_t flag, int channel, bool contribute, int replication, int blocks, int threads, int barrier_mode,
+         uintptr_t stream) {
+        zero1_reduce_scatter_launch(pt.pt, st.dev(), P<void>(mc_base), off, nelem, scale, flag, channel,
+                                    contribute ? 1 : 0, replication, blocks, threads, barrier_mode, S(stream));
+      },
+      py::arg("pt"), py::arg("status"), py::arg("mc_base"), py::arg("off"), py::arg("nelem"), py::arg("scale"),
+      py::arg("flag"), py::arg("channel"), py::arg("contribute"), py::arg("replication"), py::arg("blocks"),
+      py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
+  m.def(
+      "zero1_commit",
+      [](const PeerTableH& pt, const Status& st, uintptr_t gate, uint64_t flag, uint32_t seq, int channel,
+         bool host_ok, bool exchange, uintptr_t stream) {
+        zero1_commit_launch(pt.pt, st.dev(), P<int>(gate), flag, seq, channel, host_ok ? 1 : 0, exchange ? 1 : 0,
+                            S(stream));
+      },
+      py::arg("pt"), py::arg("status"), py::arg("gate"), py::arg("flag"), py::arg("seq"), py::arg("channel"),
+      py::arg("host_ok"), py::arg("exchange"), py::arg("stream"));
+  m.def(
+      "zero1_adamw_allgather",
+      [](const PeerTableH& pt, const Status& st, uintptr_t mc_base, uintptr_t gate, size_t poff, uintptr_t grad,
+         uintptr_t master, uintptr_t mm, uintptr_t v, size_t nelem, float lr, float b1, float b2, float eps,
+         float wd, uint64_t flag, int channel, int replication, int mode, int blocks, int threads,
+         int barrier_mode, uintptr_t stream) {
+        zero1_adamw_allgather_launch(pt.pt, st.dev(), P<void>(mc_base), P<const int>(gate), poff, P<void>(grad),
+                                     P<float>(master), P<float>(mm), P<float>(v), nelem, lr, b1, b2, eps, wd,
+                                     flag, channel, replication, mode, blocks, threads, barrier_mode, S(stream));
+      },
+      py::arg("pt"), py::arg("status"), py::arg("mc_base"), py::arg("gate"), py::arg("poff"), py::arg("grad"),
+      py::arg("master"), py::arg("m"), py::arg("v"), py::arg("nelem"), py::arg("lr"), py::arg("b1"),
+      py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("flag"), py::arg("channel"), py::arg("replication"),
+      py::arg("mode"), py::arg("blocks"), py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
 
   m.def("q8_ngroups", &q8_ngroups);
   m.def("q8_buffer_bytes", &q8_buffer_bytes);

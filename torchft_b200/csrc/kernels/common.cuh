@@ -35,7 +35,11 @@ struct StatusBlock {
   volatile uint32_t error_seq;    // low 32 bits of the flag we waited for
   volatile uint64_t timeout_ns;   // host -> device: spin budget per wait
   volatile uint64_t launches;     // device -> host: kernels completed (debug)
+  // device -> host: commit verdicts of the device-side commit kernel (zero1.cu). Slot seq % ring
+  // holds (seq << 1) | verdict, so the host can tell a stale slot from the one it is waiting for.
+  volatile uint32_t verdict[64];
 };
+constexpr uint32_t kVerdictRing = 64;
 
 enum ErrCode : uint32_t { kOk = 0, kErrTimeout = 1, kErrAborted = 2 };
 

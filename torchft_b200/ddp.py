@@ -86,14 +86,19 @@ class FlatDistributedDataParallel(nn.Module):
     """
 
     def __init__(self, manager: "Manager", module: nn.Module, flat: Any, bucket_mb: float = 256.0,
-                 should_quantize: bool = False) -> None:
+                 should_quantize: bool = False, bucket_ranges: Any = None, reduce_fn: Any = None) -> None:
+        """``bucket_ranges`` (element ranges tiling the flat buffer) overrides the size-based bucketing and
+        ``reduce_fn(bucket_index, start, end) -> Work`` replaces the plain ``manager.allreduce`` -- the FT-ZeRO-1
+        trainer passes one bucket per optimizer unit and a reduce-scatter."""
         super().__init__()
         self.module = module
         self._manager = manager
         self._flat = flat
         self._quantize = should_quantize
+        self._reduce_fn = reduce_fn
         bucket_elems = max(1, int(bucket_mb * (1 << 20)) // flat.grad.element_size())
-        self._buckets: "List[Tuple[int, int, List[nn.Parameter]]]" = flat.buckets(bucket_elems)
+        self._buckets: "List[Tuple[int, int, List[nn.Parameter]]]" = (
+            flat.buckets_from_ranges(bucket_ranges) if bucket_ranges is not None else flat.buckets(bucket_elems))
         self._pending: List[int] = []
         self._works: List[Any] = []
         self._param_bucket: Dict[int, int] = {}
@@ -113,14 +118,20 @@ class FlatDistributedDataParallel(nn.Module):
         bi = self._param_bucket[id(p)]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
-            start, end, _ = self._buckets[bi]
-            self._works.append(self._manager.allreduce(self._flat.grad[start:end], should_quantize=self._quantize))
+            self._works.append(self._reduce(bi))
+
+    def _reduce(self, bi: int) -> Any:
+        start, end, _ = self._buckets[bi]
+        if self._reduce_fn is not None:
+            return self._reduce_fn(bi, start, end)
+        return self._manager.allreduce(self._flat.grad[start:end], should_quantize=self._quantize)
 
     def forward(self, *args: object, **kwargs: object) -> object:
         return self.module(*args, **kwargs)
 
-    def finish(self) -> None:
-        """Make the current stream wait for every bucket reduction issued by this backward."""
+    def finish(self, wait: bool = True) -> None:
+        """Make the current stream wait for every bucket reduction issued by this backward (``wait=False``:
+        only issue the missing ones; whoever consumes the gradients orders itself behind the comm stream)."""
         # parameters that received no gradient this step still need their bucket reduced
         for bi, left in enumerate(self._pending):
             if left > 0:
@@ -128,9 +139,10 @@ class FlatDistributedDataParallel(nn.Module):
                 for q in params:
                     if q.grad is None:
                         self._flat.adopt_grad(q)  # unused parameter this step: contributes zeros
-                self._works.append(self._manager.allreduce(self._flat.grad[start:end], should_quantize=self._quantize))
-        for w in self._works:
-            w.wait()
+                self._works.append(self._reduce(bi))
+        if wait:
+            for w in self._works:
+                w.wait()
         self._reset()
 
     @property

@@ -1,25 +1,29 @@
 """Per-rank fault-tolerance state machine.
 
-One ``Manager`` per training process. Per step (reference
-semantics: /root/reference/torchft/manager.py:148-1053):
+One ``Manager`` per training process. A training step is three calls (semantics of
+/root/reference/torchft/manager.py:148-1053):
 
-1. ``start_quorum()``  - async (overlaps the forward pass): group barrier +
-   Lighthouse quorum through the C++ ``ManagerServer``; on a quorum-id change
-   the process group is *reconfigured* (peer-memory remap on ``ProcessGroupB200``);
-   replicas behind ``max_step`` heal from an up-to-date peer via the checkpoint
-   transport (NVLink P2P by default on CUDA).
-2. ``allreduce()``     - fault-tolerant gradient reduction; errors are swallowed and
-   latched, never raised. On ``ProcessGroupB200`` the 1/num_participants scale and
-   the non-participant zero contribution are fused into the all-reduce kernel.
-3. ``should_commit()`` - intra-group AND barrier; the optimizer steps only when
-   every rank of the group saw no error and enough replicas participated.
+1. ``start_quorum()``  -- async by default (overlaps the forward pass): intra-group barrier + Lighthouse
+   quorum through the C++ ``ManagerServer``; when the quorum id changed the process group is
+   *reconfigured* (a peer-memory remap on ``ProcessGroupB200``); replicas behind ``max_step`` heal from
+   an up-to-date peer through the checkpoint transport.
+2. ``allreduce()`` / ``guarded()`` -- fault-tolerant collectives: errors never raise, the first one is
+   latched, later calls become no-ops and the step is discarded.
+3. a commit decision, in one of two forms:
 
-B200-specific departures from the reference:
+   * ``should_commit()`` -- the reference's host-synchronous form: drain the stream, AND over the ranks
+     of the group through the ManagerServer, return a bool.
+   * ``commit_on_device(committer)`` -- B200-native form for replica groups of ONE rank: the verdict is
+     computed by a kernel (``zero1_commit_kernel``: AND of "no latched error, enough participants" over
+     the quorum through the NVLink signal pads), lands in a device gate word that the fused optimizer
+     kernels test, and the host learns it LAZILY -- on the quorum thread at the next ``start_quorum``,
+     or whenever ``current_step()`` is asked. No ``cudaStreamSynchronize`` and no RPC on the step's
+     critical path (the reference does both every step, manager.py:884-903).
 
-* the commit path synchronises only the streams that carry collectives/recovery
-  (events), not the whole device;
-* ``commit_gate`` exposes the verdict as a device int32 so a fused optimizer
-  kernel can be gated without further host round trips.
+Bookkeeping (step counter, batches committed, consecutive failures, structured commit log) lives in
+``_StepLedger`` and is identical for both forms. A ``_LivenessWatch`` thread turns "the Lighthouse no
+longer hears replica X" into ``pg.abort()`` so kernels spinning on a dead peer bail out after the
+heartbeat timeout instead of the (much longer) collective timeout.
 """
 
 from __future__ import annotations
@@ -28,13 +32,15 @@ import concurrent.futures
 import logging
 import os
 import socket
+import threading
 import traceback
 import uuid
 import weakref
 from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
 from datetime import timedelta
 from enum import Enum
-from typing import TYPE_CHECKING, Callable, Dict, List, Optional, TypeVar, cast
+from typing import TYPE_CHECKING, Any, Callable, Dict, List, Optional, TypeVar, cast
 
 import torch
 from torch.distributed import ReduceOp, TCPStore, Work
@@ -61,6 +67,7 @@ QUORUM_TIMEOUT_SEC_ENV = "TORCHFT_QUORUM_TIMEOUT_SEC"
 CONNECT_TIMEOUT_SEC_ENV = "TORCHFT_CONNECT_TIMEOUT_SEC"
 QUORUM_RETRIES_ENV = "TORCHFT_QUORUM_RETRIES"
 TORCH_FR_DUMP_TEMP_FILE_ENV = "TORCH_FR_DUMP_TEMP_FILE"
+LIVENESS_ENV = "TORCHFT_B200_LIVENESS_ABORT"
 
 T = TypeVar("T")
 S = TypeVar("S")
@@ -73,13 +80,10 @@ def get_timeout(timeout_sec_env: Optional[str], default_timeout: timedelta) -> t
 
 def extract_trailing_digits(s: str) -> int:
     """``"replica_12"`` -> 12; 0 when the string does not end in digits."""
-
-    digits = ""
-    for ch in reversed(s):
-        if not ch.isdigit():
-            break
-        digits = ch + digits
-    return int(digits) if digits else 0
+    n = len(s)
+    while n > 0 and s[n - 1].isdigit():
+        n -= 1
+    return int(s[n:]) if n < len(s) else 0
 
 
 class WorldSizeMode(Enum):
@@ -95,7 +99,7 @@ class WorldSizeMode(Enum):
 
 
 class ExceptionWithTraceback(Exception):
-    """Wraps the first error reported in a step together with its formatted traceback (reference: manager.py:141-145)."""
+    """The first error reported in a step, with the traceback that was live when it was reported."""
 
     def __init__(self, e: Exception) -> None:
         self.original_exception = e
@@ -103,6 +107,95 @@ class ExceptionWithTraceback(Exception):
         super().__init__(f"{e}\n{self.stack_trace}")
 
 
+# --------------------------------------------------------------------------- small state holders
+@dataclass
+class _Participation:
+    """Who reduces with whom this step, derived from one quorum result."""
+
+    rank: Optional[int] = None   # this replica's index among the contributors (None: spare / behind)
+    world: int = 0               # number of contributors (the AVG divisor)
+
+    @staticmethod
+    def derive(quorum: Any, everyone_counts: bool, mode: WorldSizeMode, cap: int) -> "_Participation":
+        # async quorum (or healing disabled): only replicas already at max_step contribute; a replica
+        # that heals eagerly (sync quorum) counts right away
+        rank, world = ((quorum.replica_rank, quorum.replica_world_size) if everyone_counts
+                       else (quorum.max_replica_rank, quorum.max_world_size))
+        if mode == WorldSizeMode.FIXED_WITH_SPARES:
+            world = min(world, cap)
+            if rank is not None and rank >= cap:
+                rank = None
+        return _Participation(rank, world)
+
+
+class _StepLedger:
+    """Step counter, committed batches and consecutive commit failures + the structured commit log."""
+
+    def __init__(self, max_retries: Optional[int]) -> None:
+        self.step = 0
+        self.batches = 0
+        self.failures = 0
+        self._max_retries = max_retries
+        self._log = logging.getLogger("torchft_commits")
+
+    def record(self, committed: bool, participants: int, tags: Dict[str, object]) -> None:
+        self._log.info("", extra={**tags, "step": self.step, "commit_result": committed})
+        if committed:
+            self.step += 1
+            self.batches += participants
+            self.failures = 0
+            return
+        self.failures += 1
+        if self._max_retries is not None and self.failures > self._max_retries:
+            raise RuntimeError(f"should_commit failed {self.failures} times consecutively, exceeding max_retries={self._max_retries}")
+
+
+@dataclass
+class _DeferredCommit:
+    committer: Any
+    seq: int
+    participants: int
+    tags: Dict[str, object]
+
+
+class _LivenessWatch(threading.Thread):
+    """Polls the Lighthouse's heartbeat table and calls ``on_dead`` when a member of the current quorum
+    stopped heart-beating -- the data plane's spins are then released by ``pg.abort()`` within about one
+    heartbeat timeout (the reference's analogue: user-space timeout -> ``ncclCommAbort``,
+    process_group.py:738-763, which only fires after the full collective timeout)."""
+
+    def __init__(self, lighthouse_addr: str, members: Callable[[], List[str]], on_dead: Callable[[str], None]) -> None:
+        super().__init__(name="torchft_liveness", daemon=True)
+        self._addr = lighthouse_addr
+        self._members = members
+        self._on_dead = on_dead
+        self._halt = threading.Event()
+        self.period_s = 0.5
+
+    def run(self) -> None:
+        from torchft_b200.coordination import lighthouse_status
+
+        while not self._halt.wait(self.period_s):
+            members = self._members()
+            if len(members) < 2:
+                continue
+            try:
+                st = lighthouse_status(self._addr, timedelta(seconds=2))
+            except Exception:  # noqa: BLE001 - the lighthouse being away is not a peer failure
+                continue
+            self.period_s = max(0.05, min(1.0, float(st.get("heartbeat_timeout_ms", 5000)) / 4000.0))
+            beats = st.get("heartbeats", {})
+            for rid in members:
+                hb = beats.get(rid)
+                if hb is not None and not hb.get("alive", True):
+                    self._on_dead(rid)
+                    break
+
+    def stop(self) -> None:
+        self._halt.set()
+
+
+# --------------------------------------------------------------------------- the manager
 class Manager:
     """Fault-tolerant training-loop manager (see module docstring).
 
@@ -150,7 +243,8 @@ class Manager:
             lighthouse_addr: (group rank 0) lighthouse address (env TORCHFT_LIGHTHOUSE)
             replica_id: (group rank 0) human-readable id; a uuid suffix makes restarts unique
             port: (group rank 0) manager server port (env TORCHFT_MANAGER_PORT, else ephemeral)
-            checkpoint_transport: heal transport; default P2P over NVLink on CUDA, HTTP on CPU
+            checkpoint_transport: heal transport; default NVLink P2P when ``pg`` is a ``ProcessGroupB200``
+                (one NVSwitch domain by construction), HTTP otherwise (works across hosts)
             init_sync: force a step-0 weight sync from the primary replica
             max_retries: raise after this many consecutive failed commits (None = never)
             quorum_retries: lighthouse quorum retries before the manager gives up
@@ -159,48 +253,45 @@ class Manager:
         self.commits_logger = logging.getLogger("torchft_commits")
         self.errors_logger = logging.getLogger("torchft_errors")
 
-        self._load_state_dict_fns: Dict[str, Callable[[object], None]] = {}
-        self._user_state_dicts: Dict[str, Callable[[], object]] = {}
-        self._original_fr_dump_temp_file = os.environ.get(TORCH_FR_DUMP_TEMP_FILE_ENV)
         self._replica_id = replica_id
-
         self._timeout = get_timeout(os.environ.get(TIMEOUT_SEC_ENV), timeout)
         self._quorum_timeout = get_timeout(os.environ.get(QUORUM_TIMEOUT_SEC_ENV), quorum_timeout)
         self._connect_timeout = get_timeout(os.environ.get(CONNECT_TIMEOUT_SEC_ENV), connect_timeout)
         self._quorum_retries = int(os.environ.get(QUORUM_RETRIES_ENV, str(quorum_retries)))
+        self._original_fr_dump_temp_file = os.environ.get(TORCH_FR_DUMP_TEMP_FILE_ENV)
 
+        # user state: key -> (load, save); reads of it (heal sends) are fenced by a reader-writer lock
+        self._state_fns: Dict[str, tuple] = {}
         self._state_dict_lock = RWLock(timeout=self._timeout.total_seconds())
-        self._is_state_dict_read_allowed = True
+        self._state_reads_allowed = True
         if load_state_dict and state_dict:
             self.register_state_dict_fn("default", load_state_dict, state_dict)
 
-        self._pending_state_dict: Optional[Dict[str, object]] = None
+        self._pg = pg
         self._use_async_quorum = use_async_quorum
-        self._replica_world_size_mode = world_size_mode
+        self._world_size_mode = world_size_mode
         self._init_sync = init_sync
-        self._max_retries = max_retries
-        self._commit_failures = 0
+        self._min_replica_size = min_replica_size
+        self._ledger = _StepLedger(max_retries)
+        self._ledger_lock = threading.RLock()
+        self._deferred: Optional[_DeferredCommit] = None
 
         store_addr = store_addr or os.environ["MASTER_ADDR"]
         store_port = store_port or int(os.environ["MASTER_PORT"])
         self._group_rank = rank if rank is not None else int(os.environ["RANK"])
         self._group_world_size = world_size or int(os.environ["WORLD_SIZE"])
-        self._min_replica_size = min_replica_size
 
-        if checkpoint_transport is None:
-            checkpoint_transport = self._default_transport()
-        self._checkpoint_transport: CheckpointTransport[Dict[str, T]] = checkpoint_transport
+        self._checkpoint_transport: CheckpointTransport[Dict[str, T]] = (
+            checkpoint_transport if checkpoint_transport is not None else self._default_transport())
 
         self._executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="async_quorum")
         self._quorum_future: Optional[concurrent.futures.Future] = None
-
         self._store = TCPStore(host_name=store_addr, port=store_port, is_master=False, wait_for_workers=False)
-        self._pg = pg
         self._manager: Optional[ManagerServer] = None
-
         self._recovery_stream: Optional[torch.cuda.Stream] = torch.cuda.Stream() if torch.cuda.is_available() else None
         self._recovery_event: Optional[torch.cuda.Event] = None
         self._commit_gate: Optional[torch.Tensor] = None
+        self._liveness: Optional[_LivenessWatch] = None
 
         if self._group_rank == 0:
             if port is None:
@@ -225,16 +316,16 @@ class Manager:
 
         addr = self._store.get(MANAGER_ADDR_KEY).decode("utf-8")
         self._client = ManagerClient(addr, connect_timeout=self._connect_timeout)
-        full_replica_id = self._store.get(REPLICA_ID_KEY).decode("utf-8")
-        self._logger = _ManagerLogger(self, full_replica_id or "", self._group_rank)
+        self._full_replica_id = self._store.get(REPLICA_ID_KEY).decode("utf-8")
+        self._logger = _ManagerLogger(self, self._full_replica_id or "", self._group_rank)
 
-        self._step = 0
         self._quorum_id = -1
+        self._quorum_members: List[str] = []
         self._errored: Optional[ExceptionWithTraceback] = None
         self._healing = False
-        self._batches_committed = 0
-        self._participating_replica_rank: Optional[int] = None
-        self._participating_replica_world_size = 0
+        self._serving_heal = False
+        self._pending_state_dict: Optional[Dict[str, object]] = None
+        self._participation = _Participation()
 
         self._global_rank = (
             self._group_rank
@@ -243,12 +334,23 @@ class Manager:
         )
         self._update_fr_path()
 
+        want_watch = os.environ.get(LIVENESS_ENV)
+        if (want_watch != "0" and lighthouse_addr and getattr(pg, "supports_liveness_abort", False) is True) or want_watch == "1":
+            if lighthouse_addr:
+                self._liveness = _LivenessWatch(lighthouse_addr, self._peers_in_quorum, self._peer_died)
+                self._liveness.start()
+
+    # ------------------------------------------------------------------ transports / state hooks
     def _default_transport(self) -> CheckpointTransport[Dict[str, T]]:
-        if torch.cuda.is_available() and os.environ.get("TORCHFT_B200_TRANSPORT", "p2p") == "p2p":
+        # CUDA-IPC handles only open on the exporting host: pick the NVLink transport only when the process
+        # group itself is confined to one NVSwitch domain (ProcessGroupB200); everything else gets the HTTP
+        # transport, which works across hosts like the reference's default (manager.py:277-281)
+        choice = os.environ.get("TORCHFT_B200_TRANSPORT", "auto")
+        same_host = getattr(self._pg, "single_host", False) is True
+        if torch.cuda.is_available() and (choice == "p2p" or (choice == "auto" and same_host)):
             from torchft_b200.checkpointing.p2p_transport import P2PTransport
 
-            # receive IN PLACE into the live tensors: a heal allocates nothing (a second copy
-            # of an 8B model + optimizer state does not fit next to the first in 180 GB)
+            # receive IN PLACE into the live tensors: a heal allocates nothing
             return P2PTransport(timeout=self._timeout, state_dict=self._heal_targets)
         from torchft_b200.checkpointing.http_transport import HTTPTransport
 
@@ -256,109 +358,127 @@ class Manager:
 
     def _heal_targets(self) -> Dict[str, object]:
         """Same pytree shape as ``_manager_state_dict`` (destinations for an in-place heal)."""
-        return {"user": {k: fn() for k, fn in self._user_state_dicts.items()}, "torchft": self.state_dict()}
-
-    # ------------------------------------------------------------ state dict
-    def allow_state_dict_read(self) -> None:
-        if not self._is_state_dict_read_allowed:
-            self._is_state_dict_read_allowed = True
-            self._state_dict_lock.w_release()
-
-    def disallow_state_dict_read(self) -> None:
-        if self._is_state_dict_read_allowed:
-            self._is_state_dict_read_allowed = False
-            self._state_dict_lock.w_acquire()
+        return {"user": {k: save() for k, (_, save) in self._state_fns.items()}, "torchft": self.state_dict()}
 
     def register_state_dict_fn(self, key: str, load_state_dict: Callable[[T], None], state_dict: Callable[[], T]) -> None:
-        assert key not in self._load_state_dict_fns and key not in self._user_state_dicts, f"duplicate state_dict key {key}"
-        self._load_state_dict_fns[key] = cast(Callable[[object], None], load_state_dict)
-        self._user_state_dicts[key] = state_dict
+        """Add a named piece of user state that travels with live heals."""
+        assert key not in self._state_fns, f"duplicate state_dict key {key}"
+        self._state_fns[key] = (cast(Callable[[object], None], load_state_dict), state_dict)
 
     def set_state_dict_fns(self, load_state_dict: Callable[[T], None], state_dict: Callable[[], T]) -> None:
         self._logger.warn("`set_state_dict_fns` is deprecated, please use `register_state_dict_fn` instead")
         self.register_state_dict_fn("set_state_dict_fns", load_state_dict, state_dict)
 
+    def allow_state_dict_read(self) -> None:
+        """Let heal senders read the user state again (after an optimizer step)."""
+        if self._state_reads_allowed:
+            return
+        self._state_reads_allowed = True
+        self._state_dict_lock.w_release()
+
+    def disallow_state_dict_read(self) -> None:
+        """Fence heal senders out while the user state is being modified."""
+        if not self._state_reads_allowed:
+            return
+        self._state_reads_allowed = False
+        self._state_dict_lock.w_acquire()
+
+    def _manager_state_dict(self) -> Dict[str, object]:
+        with self._state_dict_lock.r_lock():
+            assert self._state_fns, "user state_dict is not initialized."
+            return {"user": {k: save() for k, (_, save) in self._state_fns.items()}, "torchft": self.state_dict()}
+
     def shutdown(self, wait: bool = True) -> None:
-        """Stop the checkpoint transport, the manager server and the quorum thread."""
+        """Stop the liveness watch, the checkpoint transport, the manager server and the quorum thread."""
+        if self._liveness is not None:
+            self._liveness.stop()
         self._checkpoint_transport.shutdown(wait=wait)
         if self._manager is not None:
             self._manager.shutdown()
         self._executor.shutdown(wait=wait)
 
-    # -------------------------------------------------------------- allreduce
+    # ------------------------------------------------------------------ collectives
+    def guarded(self, launch: Callable[[], Optional[Work]], value: object = None) -> Work:
+        """Run ``launch()`` (which enqueues a collective of the fault-tolerant group and returns its ``Work``)
+        under this step's error latch: after a first error nothing is launched any more, an exception is
+        latched instead of raised, and the returned work's ``wait()`` never raises."""
+        if self.errored():
+            return DummyWork(value)
+        self.wait_quorum()
+        try:
+            work = launch()
+            return DummyWork(value) if work is None else _ManagedWork(self, work, value)
+        except Exception as e:  # noqa: BLE001
+            self._logger.exception(f"got exception in collective -- skipping remaining: {e}")
+            self.report_error(e)
+            return DummyWork(value)
+
     @torch.profiler.record_function("torchft::manager::allreduce")
     def allreduce(self, tensor: torch.Tensor, should_quantize: bool = False, reduce_op: ReduceOp = ReduceOp.AVG) -> Work:
         """Fault-tolerant all-reduce across the participating replicas.
 
         AVG divides by ``num_participants()``. Errors never raise: the first one is
         latched (``errored()``), the returned work completes, later calls are
-        no-ops, and ``should_commit`` will return False so the (possibly
+        no-ops, and the commit decision will be negative so the (possibly
         corrupted) tensor is discarded.
         """
-        if self.errored():
-            return DummyWork(tensor)
-        self.wait_quorum()
-        num_participants = self.num_participants()
-        participating = self.is_participating()
+        if reduce_op == ReduceOp.AVG and not torch.is_floating_point(tensor):
+            raise ValueError("average reduce op is only supported for floating point tensors")
 
-        pg_op = reduce_op
-        if reduce_op == ReduceOp.AVG:
-            if not torch.is_floating_point(tensor):
-                raise ValueError("average reduce op is only supported for floating point tensors")
-            pg_op = ReduceOp.SUM
-
-        try:
-            native = self._native_allreduce(tensor, should_quantize, reduce_op, num_participants, participating)
-            if native is not None:
-                return _ManagedWork(self, native, tensor)
-
-            if not participating:
+        def launch() -> Work:
+            n, contributing = self.num_participants(), self.is_participating()
+            fused = self._fused_allreduce(tensor, should_quantize, reduce_op, n, contributing)
+            if fused is not None:
+                return fused
+            # generic process group: zero a non-contributor, SUM, divide afterwards
+            if not contributing:
                 tensor.zero_()
+            wire_op = ReduceOp.SUM if reduce_op == ReduceOp.AVG else reduce_op
             if should_quantize and tensor.is_cuda:
                 from torchft_b200.collectives import allreduce_quantized
 
-                work = allreduce_quantized([tensor], pg_op, self._pg, torch.cuda.current_stream())
-            else:
-                opts = AllreduceOptions()
-                opts.reduceOp = pg_op
-                work = self._pg.allreduce([tensor], opts)
+                return allreduce_quantized([tensor], wire_op, self._pg, torch.cuda.current_stream())
+            opts = AllreduceOptions()
+            opts.reduceOp = wire_op
+            return self._pg.allreduce([tensor], opts)
 
-            managed = _ManagedWork(self, work, tensor)
-            if reduce_op == ReduceOp.AVG:
+        fused_path = self._has_fused_path(tensor, reduce_op)
+        work = self.guarded(launch, tensor)
+        if reduce_op == ReduceOp.AVG and not fused_path and isinstance(work, _ManagedWork):
+            n = self.num_participants()
 
-                @torch.profiler.record_function("torchft::manager::allreduce::callback")
-                def normalize(fut: Future) -> torch.Tensor:
-                    tensor.div_(num_participants)
-                    return tensor
+            @torch.profiler.record_function("torchft::manager::allreduce::callback")
+            def normalize(fut: Future) -> torch.Tensor:
+                tensor.div_(n)
+                return tensor
 
-                managed.get_future().then(normalize)
-            return managed
-        except Exception as e:  # noqa: BLE001
-            self._logger.exception(f"got exception in all reduce -- skipping remaining: {e}")
-            self.report_error(e)
-            return DummyWork(tensor)
+            work.get_future().then(normalize)
+        return work
 
-    def _native_allreduce(self, tensor: torch.Tensor, should_quantize: bool, reduce_op: ReduceOp,
-                          num_participants: int, participating: bool) -> Optional[Work]:
-        """Fused path on ProcessGroupB200: scale + zero-contribution live inside the kernel."""
+    _FUSED_OPS = (ReduceOp.SUM, ReduceOp.AVG, ReduceOp.MAX, ReduceOp.MIN)
+
+    def _has_fused_path(self, tensor: torch.Tensor, reduce_op: ReduceOp) -> bool:
         pg = self._pg
-        fused = getattr(pg, "allreduce_native", None)
-        if fused is None or not tensor.is_cuda or not pg._native_ok(tensor):  # type: ignore[attr-defined]
+        return (getattr(pg, "allreduce_native", None) is not None and tensor.is_cuda and reduce_op in self._FUSED_OPS
+                and pg._native_ok(tensor))  # type: ignore[attr-defined]
+
+    def _fused_allreduce(self, tensor: torch.Tensor, should_quantize: bool, reduce_op: ReduceOp,
+                         num_participants: int, participating: bool) -> Optional[Work]:
+        """ProcessGroupB200: 1/num_participants and the zero contribution live inside the kernel."""
+        if not self._has_fused_path(tensor, reduce_op):
             return None
         from torchft_b200.ops import _native
 
-        ops = {ReduceOp.SUM: _native.OP_SUM, ReduceOp.AVG: _native.OP_SUM, ReduceOp.MAX: _native.OP_MAX, ReduceOp.MIN: _native.OP_MIN}
-        if reduce_op not in ops:
-            return None
+        pg = self._pg
         scale = 1.0 / max(num_participants, 1) if reduce_op == ReduceOp.AVG else 1.0
         if should_quantize and reduce_op in (ReduceOp.SUM, ReduceOp.AVG):
             return pg.allreduce_q8(tensor, tensor, None, scale=scale, contribute=participating)  # type: ignore[attr-defined]
-        return fused(tensor, op=ops[reduce_op], scale=scale, contribute=participating)
+        code = {ReduceOp.MAX: _native.OP_MAX, ReduceOp.MIN: _native.OP_MIN}.get(reduce_op, _native.OP_SUM)
+        return pg.allreduce_native(tensor, op=code, scale=scale, contribute=participating)  # type: ignore[attr-defined]
 
     def alloc_symmetric(self, name: str, nbytes: int) -> Optional[torch.Tensor]:
         """Peer-visible buffer from the process group (``ProcessGroupB200.alloc_symmetric``) or ``None``
-        when the group has no such memory. Tensors carved from it are all-reduced in place, zero-copy.
-        Call with identical arguments on every replica before the next quorum."""
+        when the group has no such memory. Tensors carved from it are all-reduced in place, zero-copy."""
         fn = getattr(self._pg, "alloc_symmetric", None)
         return fn(name, nbytes) if callable(fn) else None
 
@@ -375,20 +495,10 @@ class Manager:
         ``torch.sub`` followed by :meth:`allreduce`. ``out`` may alias ``a``. Same
         error-latching contract as :meth:`allreduce`.
         """
-        if self.errored():
-            return DummyWork(out)
-        self.wait_quorum()
-        n = self.num_participants()
-        participating = self.is_participating()
-        try:
-            pg = self._pg
-            if should_quantize and self.supports_fused_delta() and all(pg._native_ok(t) for t in (out, a, b)):  # type: ignore[attr-defined]
-                work = pg.allreduce_q8(out, a, b, scale=1.0 / max(n, 1), contribute=participating)  # type: ignore[attr-defined]
-                return _ManagedWork(self, work, out)
-        except Exception as e:  # noqa: BLE001
-            self._logger.exception(f"got exception in allreduce_delta -- skipping remaining: {e}")
-            self.report_error(e)
-            return DummyWork(out)
+        pg = self._pg
+        if should_quantize and self.supports_fused_delta() and all(pg._native_ok(t) for t in (out, a, b)):  # type: ignore[attr-defined]
+            return self.guarded(lambda: pg.allreduce_q8(out, a, b, scale=1.0 / max(self.num_participants(), 1),  # type: ignore[attr-defined]
+                                                        contribute=self.is_participating()), out)
         torch.sub(a, b, out=out)
         return self.allreduce(out, should_quantize=should_quantize)
 
@@ -401,10 +511,9 @@ class Manager:
 
     def wrap_future(self, fut: Future, default: T, timeout: Optional[timedelta] = None) -> Future:
         """Future that never fails: errors/timeouts are reported to the manager and replaced by ``default``."""
-        fut = future_timeout(fut, timeout or self._timeout)
         stream = torch.cuda.current_stream() if torch.cuda.is_available() else None
 
-        def swallow(f: Future) -> T:
+        def absorb(f: Future) -> T:
             with get_stream_context(stream):
                 try:
                     return f.value()
@@ -413,9 +522,9 @@ class Manager:
                     self.report_error(e)
                     return default
 
-        return fut.then(swallow)
+        return future_timeout(fut, timeout or self._timeout).then(absorb)
 
-    # ----------------------------------------------------------------- quorum
+    # ------------------------------------------------------------------ quorum
     def start_quorum(self, allow_heal: bool = True, shrink_only: bool = False, timeout: Optional[timedelta] = None) -> None:
         """Begin a new step: compute the quorum (async by default) and ready the group.
 
@@ -426,18 +535,14 @@ class Manager:
             self._quorum_future.result()
         self._errored = None
         self._healing = False
-        self._quorum_future = self._executor.submit(
-            self._async_quorum,
-            allow_heal=allow_heal,
-            shrink_only=shrink_only,
-            quorum_timeout=timeout or self._quorum_timeout,
-            curr_device=torch.cuda.current_device() if torch.cuda.is_available() else -1,
-        )
+        device = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        self._quorum_future = self._executor.submit(self._quorum_task, allow_heal, shrink_only,
+                                                    timeout or self._quorum_timeout, device)
         if not self._use_async_quorum:
             self.wait_quorum()
             if self._healing:
                 # sync quorum: heal before the forward pass so this replica counts immediately
-                self._apply_pending_state_dict()
+                self._install_pending_state()
                 self._healing = False
 
     @torch.profiler.record_function("torchft::manager::wait_quorum")
@@ -447,107 +552,93 @@ class Manager:
         self._quorum_future.result()
 
     @torch.profiler.record_function("torchft::manager::_async_quorum")
-    def _async_quorum(self, allow_heal: bool, shrink_only: bool, quorum_timeout: timedelta, curr_device: int) -> None:
+    def _quorum_task(self, allow_heal: bool, shrink_only: bool, quorum_timeout: timedelta, device: int) -> None:
         try:
             torch.multiprocessing._set_thread_name("torchft_quorum")
         except Exception:  # pragma: no cover
             pass
-        if curr_device >= 0 and torch.cuda.is_available():
-            torch.cuda.set_device(curr_device)
+        if device >= 0 and torch.cuda.is_available():
+            torch.cuda.set_device(device)
+
+        # the previous step's device-side verdict decides which step number we report
+        self._settle_deferred()
 
         with torch.profiler.record_function("torchft::manager::_client::_quorum"):
+            with self._ledger_lock:
+                step, failures = self._ledger.step, self._ledger.failures
             quorum = self._client._quorum(
                 group_rank=self._group_rank,
-                step=self._step,
+                step=step,
                 checkpoint_metadata=self._checkpoint_transport.metadata(),
                 shrink_only=shrink_only,
                 timeout=quorum_timeout,
                 init_sync=self._init_sync,
-                commit_failures=self._commit_failures,
+                commit_failures=failures,
             )
 
-        quorum_id = quorum.quorum_id
-        max_step = quorum.max_step
-        heal = quorum.heal
-        ranks_in_quorum = [
-            extract_trailing_digits(rid.split(":")[0]) * self._group_world_size + self._group_rank
-            for rid in quorum.replica_ids
-        ]
+        self._participation = _Participation.derive(
+            quorum, everyone_counts=not (self._use_async_quorum or not allow_heal),
+            mode=self._world_size_mode, cap=self._min_replica_size)
+        self._quorum_members = list(quorum.replica_ids)
+        self._serving_heal = bool(allow_heal and quorum.recover_dst_replica_ranks)
 
-        # async quorum: only replicas already at max_step contribute this step;
-        # sync quorum (or no healing): everybody in the quorum does.
-        if self._use_async_quorum or not allow_heal:
-            self._participating_replica_rank = quorum.max_replica_rank
-            self._participating_replica_world_size = quorum.max_world_size
-        else:
-            self._participating_replica_rank = quorum.replica_rank
-            self._participating_replica_world_size = quorum.replica_world_size
-
-        if self._replica_world_size_mode == WorldSizeMode.FIXED_WITH_SPARES:
-            self._participating_replica_world_size = min(self._participating_replica_world_size, self._min_replica_size)
-            if self._participating_replica_rank is not None and self._participating_replica_rank >= self._min_replica_size:
-                self._participating_replica_rank = None
-
-        if quorum_id != self._quorum_id:
-            self.quorum_logger.info("", extra={
-                "job_id": os.environ.get("JOB_ID", "unknown"), "replica_id": self._replica_id,
-                "rank": self._group_rank, "quorum_id": quorum_id, "step": max_step})
-            store_prefixed_addr = f"{quorum.store_address}/torchft/{quorum_id}/{self._group_rank}"
-            self._logger.info(f"reconfiguring for {quorum_id=} {store_prefixed_addr=}")
-            try:
-                self._quorum_id = quorum_id
-                with torch.profiler.record_function("torchft::manager::_pg::configure"):
-                    self._pg.configure(
-                        store_prefixed_addr,
-                        self._replica_id if self._replica_id is not None else "0",
-                        quorum.replica_rank,
-                        quorum.replica_world_size,
-                        quorum_id,
-                        self._group_rank,
-                        self._group_world_size,
-                        ranks_in_quorum,
-                    )
-                self._update_fr_path()
-                reset = getattr(torch._C._distributed_c10d, "_reset_fr_recording_nccl", None)
-                if reset is not None and "nccl" in self._pg.getBackendName():
-                    reset()
-            except Exception as e:  # noqa: BLE001
-                self._logger.exception(f"got exception in pg configure: {e}")
-                self.report_error(e)
-                return
-
+        if quorum.quorum_id != self._quorum_id and not self._reconfigure(quorum):
+            return
         if allow_heal:
-            with get_stream_context(self._recovery_stream):
-                try:
-                    if quorum.recover_dst_replica_ranks:
-                        self._logger.info(f"peers need recovery from us {quorum.recover_dst_replica_ranks}")
-                        with torch.profiler.record_function("torchft::manager::_checkpoint_transport::send_checkpoint"):
-                            self._checkpoint_transport.send_checkpoint(
-                                dst_ranks=quorum.recover_dst_replica_ranks,
-                                step=max_step,
-                                state_dict=self._manager_state_dict(),
-                                timeout=self._timeout,
-                            )
-                    if heal:
-                        self._healing = True
-                        src_addr = quorum.recover_src_manager_address
-                        self._logger.info(f"healing required, fetching checkpoint metadata from {src_addr=} {max_step=}")
-                        src_client = ManagerClient(src_addr, connect_timeout=self._connect_timeout)
-                        checkpoint_metadata = src_client._checkpoint_metadata(self._group_rank, timeout=self._timeout)
-                        src_rank = quorum.recover_src_replica_rank
-                        assert src_rank is not None, "must have a recover rank when healing"
-                        with torch.profiler.record_function("torchft::manager::_checkpoint_transport::recv_checkpoint"):
-                            # staged here; the user part is applied on the main thread
-                            self._pending_state_dict = self._checkpoint_transport.recv_checkpoint(
-                                src_rank=src_rank, metadata=checkpoint_metadata, step=max_step, timeout=self._timeout)
-                        self.load_state_dict(cast(Dict[str, int], self._pending_state_dict["torchft"]))
-                        self._step = max_step
-                except Exception as e:  # noqa: BLE001
-                    self._logger.exception(f"got exception in recovery: {e}")
-                    self.report_error(e)
-                self._recovery_event = (
-                    torch.cuda.current_stream().record_event() if self._recovery_stream is not None else None
-                )
+            self._recover(quorum)
+
+    def _reconfigure(self, quorum: Any) -> bool:
+        """The quorum id changed: point the process group at the new member set. False on failure (latched)."""
+        gws = self._group_world_size
+        global_ranks = [extract_trailing_digits(rid.split(":")[0]) * gws + self._group_rank for rid in quorum.replica_ids]
+        self.quorum_logger.info("", extra={**self._log_tags(), "quorum_id": quorum.quorum_id, "step": quorum.max_step})
+        prefix = f"{quorum.store_address}/torchft/{quorum.quorum_id}/{self._group_rank}"
+        self._logger.info(f"reconfiguring for quorum_id={quorum.quorum_id} store_prefixed_addr={prefix!r}")
+        try:
+            self._quorum_id = quorum.quorum_id
+            with torch.profiler.record_function("torchft::manager::_pg::configure"):
+                self._pg.configure(prefix, self._replica_id if self._replica_id is not None else "0", quorum.replica_rank,
+                                   quorum.replica_world_size, quorum.quorum_id, self._group_rank, gws, global_ranks)
+            self._update_fr_path()
+            reset = getattr(torch._C._distributed_c10d, "_reset_fr_recording_nccl", None)
+            if reset is not None and "nccl" in self._pg.getBackendName():
+                reset()
+            return True
+        except Exception as e:  # noqa: BLE001
+            self._logger.exception(f"got exception in pg configure: {e}")
+            self.report_error(e)
+            return False
+
+    def _recover(self, quorum: Any) -> None:
+        """Serve our state to replicas that are behind and/or fetch it if we are (on the recovery stream)."""
+        transport = self._checkpoint_transport
+        with get_stream_context(self._recovery_stream):
+            try:
+                if quorum.recover_dst_replica_ranks:
+                    self._logger.info(f"peers need recovery from us {quorum.recover_dst_replica_ranks}")
+                    with torch.profiler.record_function("torchft::manager::_checkpoint_transport::send_checkpoint"):
+                        transport.send_checkpoint(dst_ranks=quorum.recover_dst_replica_ranks, step=quorum.max_step,
+                                                  state_dict=self._manager_state_dict(), timeout=self._timeout)
+                if quorum.heal:
+                    self._healing = True
+                    src = quorum.recover_src_replica_rank
+                    assert src is not None, "must have a recover rank when healing"
+                    self._logger.info(f"healing required, fetching checkpoint metadata from "
+                                      f"src_addr={quorum.recover_src_manager_address!r} max_step={quorum.max_step}")
+                    peer = ManagerClient(quorum.recover_src_manager_address, connect_timeout=self._connect_timeout)
+                    metadata = peer._checkpoint_metadata(self._group_rank, timeout=self._timeout)
+                    with torch.profiler.record_function("torchft::manager::_checkpoint_transport::recv_checkpoint"):
+                        # staged; the user part is installed on the main thread at commit time
+                        self._pending_state_dict = transport.recv_checkpoint(
+                            src_rank=src, metadata=metadata, step=quorum.max_step, timeout=self._timeout)
+                    self.load_state_dict(cast(Dict[str, int], self._pending_state_dict["torchft"]))
+                    with self._ledger_lock:
+                        self._ledger.step = quorum.max_step
+            except Exception as e:  # noqa: BLE001
+                self._logger.exception(f"got exception in recovery: {e}")
+                self.report_error(e)
+            if self._recovery_stream is not None:
+                self._recovery_event = torch.cuda.current_stream().record_event()
 
     def _update_fr_path(self) -> None:
         """Flight-recorder dumps go to ``<TORCH_FR_DUMP_TEMP_FILE>_quorum_<id>/<global_rank>``."""
@@ -556,23 +647,54 @@ class Manager:
             os.makedirs(folder, exist_ok=True)
             os.environ[TORCH_FR_DUMP_TEMP_FILE_ENV] = f"{folder}/{self._global_rank}"
 
-    def _apply_pending_state_dict(self) -> None:
+    def _install_pending_state(self) -> None:
+        """Main thread: hand the staged checkpoint to the user's load functions."""
         assert self._healing, "must be in healing state"
-        assert self._quorum_future is not None, "must call start_quorum before should_commit"
-        self._quorum_future.result()
-        pending = self._pending_state_dict
-        if pending is None:
+        self.wait_quorum()
+        staged, self._pending_state_dict = self._pending_state_dict, None
+        if staged is None:
             assert self.errored(), "checkpoint was not staged and no error occured"
             return
+        assert self._state_fns, "user load_state_dict is not initialized."
         self._logger.info("applying pending state dict")
-        assert len(self._load_state_dict_fns) > 0, "user load_state_dict is not initialized."
-        user = cast(Dict[str, object], pending["user"])
-        for key, fn in self._load_state_dict_fns.items():
-            fn(user[key])
-        self._pending_state_dict = None
+        user = cast(Dict[str, object], staged["user"])
+        for key, (load, _) in self._state_fns.items():
+            load(user[key])
         self._logger.info("Loaded state dict.")
 
-    # ----------------------------------------------------------------- commit
+    # ------------------------------------------------------------------ liveness
+    def _peers_in_quorum(self) -> List[str]:
+        return [rid for rid in self._quorum_members if rid != self._full_replica_id]
+
+    def _peer_died(self, replica_id: str) -> None:
+        if self._pg.errored() is None:
+            self._logger.warn(f"lighthouse lost the heartbeat of {replica_id}: aborting in-flight collectives")
+            self.errors_logger.info("", extra={**self._log_tags(), "quorum_id": self._quorum_id, "step": self._ledger.step,
+                                               "error": f"peer {replica_id} stopped heart-beating"})
+        self._pg.abort()
+
+    # ------------------------------------------------------------------ commit
+    def _log_tags(self) -> Dict[str, object]:
+        return {"job_id": os.environ.get("JOB_ID", "unknown"), "replica_id": self._replica_id, "rank": self._group_rank}
+
+    def _drain_and_collect_errors(self) -> None:
+        """Host-synchronous prelude of a commit: recovery stream, current stream, latched PG error, staged heal."""
+        with torch.profiler.record_function("torchft::manager::should_commit::recovery_stream::synchronize"):
+            ev, self._recovery_event = self._recovery_event, None
+            if ev is not None:
+                ev.synchronize()
+        with torch.profiler.record_function("torchft::manager::should_commit::current_stream::synchronize"):
+            if torch.cuda.is_available():
+                synchronize()
+        err = self._pg.errored()
+        if err:
+            self.report_error(err)
+        if self._healing:
+            self._install_pending_state()
+
+    def _local_verdict(self) -> bool:
+        return self.num_participants() >= self._min_replica_size and self._errored is None
+
     @torch.profiler.record_function("torchft::manager::should_commit")
     def should_commit(self, timeout: Optional[timedelta] = None) -> bool:
         """Decide (identically on every rank of the group) whether to step the optimizer.
@@ -581,46 +703,67 @@ class Manager:
         when this returns True. Raises ``RuntimeError`` after more than ``max_retries``
         consecutive failures.
         """
-        with torch.profiler.record_function("torchft::manager::should_commit::recovery_stream::synchronize"):
-            if self._recovery_event is not None:
-                self._recovery_event.synchronize()
-                self._recovery_event = None
-        with torch.profiler.record_function("torchft::manager::should_commit::current_stream::synchronize"):
-            if torch.cuda.is_available():
-                synchronize()
-
-        if err := self._pg.errored():
-            self.report_error(err)
-
-        if self._healing:
-            self._apply_pending_state_dict()
-
-        enough_replicas = self.num_participants() >= self._min_replica_size
-        local_should_commit = enough_replicas and self._errored is None
-        should_commit = self._client.should_commit(self._group_rank, self._step, local_should_commit,
-                                                   timeout=timeout or self._timeout)
-        self._logger.info(f"should_commit={should_commit} enough_replicas={enough_replicas}, errored={self._errored}")
-        self.commits_logger.info("", extra={
-            "job_id": os.environ.get("JOB_ID", "unknown"), "replica_id": self._replica_id, "rank": self._group_rank,
-            "quorum_id": self._quorum_id, "step": self._step, "commit_result": should_commit})
-
+        self._settle_deferred()
+        self._drain_and_collect_errors()
+        mine = self._local_verdict()
+        verdict = self._client.should_commit(self._group_rank, self._ledger.step, mine, timeout=timeout or self._timeout)
+        self._logger.info(f"should_commit={verdict} enough_replicas={self.num_participants() >= self._min_replica_size}, "
+                          f"errored={self._errored}")
         self._checkpoint_transport.disallow_checkpoint()
-
         if self._commit_gate is not None:
-            self._commit_gate.fill_(1 if should_commit else 0)
+            self._commit_gate.fill_(1 if verdict else 0)
+        with self._ledger_lock:
+            self._ledger.record(verdict, self.num_participants(), {**self._log_tags(), "quorum_id": self._quorum_id})
+        return verdict
 
-        if should_commit:
-            self._step += 1
-            self._batches_committed += self.num_participants()
-            self._commit_failures = 0
-        else:
-            self._commit_failures += 1
-            if self._max_retries is not None and self._commit_failures > self._max_retries:
-                msg = (f"should_commit failed {self._commit_failures} times consecutively, "
-                       f"exceeding max_retries={self._max_retries}")
-                self._logger.exception(msg)
-                raise RuntimeError(msg)
-        return should_commit
+    def commit_on_device(self, committer: Any) -> Optional[bool]:
+        """Commit decision WITHOUT a host round trip (replica groups of one rank; see module docstring).
+
+        ``committer`` enqueues the verdict kernel and later reports its result::
+
+            seq = committer.enqueue(host_ok)      # kernel on the committer's stream; gate word on the device
+            committer.wait(seq, timeout) -> bool  # block the CALLING thread until the verdict is on the host
+            committer.resolved(verdict)           # bookkeeping hook once the manager has recorded it
+
+        Returns ``None`` when the verdict was deferred (normal steps) and the verdict itself when this step
+        had to be resolved synchronously (this replica is healing or is serving a checkpoint, where the
+        reference's ordering -- install state / close the checkpoint window around the decision -- matters).
+        """
+        if self._group_world_size != 1:
+            raise RuntimeError("commit_on_device needs a replica group of one rank; use should_commit()")
+        self._settle_deferred()
+        self.wait_quorum()
+        synchronous = self._healing or self._serving_heal
+        if synchronous:
+            self._drain_and_collect_errors()
+        seq = committer.enqueue(self._local_verdict())
+        with self._ledger_lock:
+            self._deferred = _DeferredCommit(committer, seq, self.num_participants(),
+                                             {**self._log_tags(), "quorum_id": self._quorum_id})
+        if not synchronous:
+            return None
+        verdict = self._settle_deferred()
+        self._checkpoint_transport.disallow_checkpoint()
+        return verdict
+
+    def _settle_deferred(self) -> Optional[bool]:
+        """Fetch the outstanding device-side verdict (if any) and book it. Safe from any thread."""
+        with self._ledger_lock:
+            d, self._deferred = self._deferred, None
+            if d is None:
+                return None
+            try:
+                verdict = bool(d.committer.wait(d.seq, self._timeout))
+            except Exception as e:  # noqa: BLE001 - a verdict that never arrives is a failed step
+                self._logger.exception(f"device commit verdict unavailable: {e}")
+                verdict = False
+            if not verdict:
+                err = self._pg.errored()
+                if err is not None:
+                    self.errors_logger.info("", extra={**d.tags, "step": self._ledger.step, "error": str(err)})
+            d.committer.resolved(verdict)
+            self._ledger.record(verdict, d.participants, d.tags)
+            return verdict
 
     def commit_gate(self) -> torch.Tensor:
         """Device int32 that ``should_commit`` sets to 1/0: lets a fused optimizer kernel be gated
@@ -630,67 +773,97 @@ class Manager:
             self._commit_gate = torch.zeros(1, dtype=torch.int32, device=dev)
         return self._commit_gate
 
-    # ------------------------------------------------------------------ state
+    # ------------------------------------------------------------------ state / accessors
     def load_state_dict(self, state_dict: Dict[str, int]) -> None:
-        self._step = state_dict["step"]
-        self._batches_committed = state_dict["batches_committed"]
-
-    def _manager_state_dict(self) -> Dict[str, object]:
-        with self._state_dict_lock.r_lock():
-            assert len(self._user_state_dicts) > 0, "user state_dict is not initialized."
-            return {"user": {k: fn() for k, fn in self._user_state_dicts.items()}, "torchft": self.state_dict()}
+        with self._ledger_lock:
+            self._ledger.step = state_dict["step"]
+            self._ledger.batches = state_dict["batches_committed"]
 
     def state_dict(self) -> Dict[str, int]:
         """``{"step", "batches_committed"}`` -- persist with your periodic checkpoints."""
-        return {"step": self._step, "batches_committed": self._batches_committed}
+        self._settle_deferred()
+        return {"step": self._ledger.step, "batches_committed": self._ledger.batches}
 
     def current_step(self) -> int:
-        return self._step
+        """Committed steps so far (resolves an outstanding device-side verdict first)."""
+        self._settle_deferred()
+        return self._ledger.step
 
     def batches_committed(self) -> int:
         """Total batches committed across all replicas and steps."""
-        return self._batches_committed
+        self._settle_deferred()
+        return self._ledger.batches
+
+    # kept as attributes of long standing (tests and user code read them)
+    @property
+    def _step(self) -> int:
+        return self._ledger.step
+
+    @_step.setter
+    def _step(self, v: int) -> None:
+        self._ledger.step = v
+
+    @property
+    def _batches_committed(self) -> int:
+        return self._ledger.batches
+
+    @property
+    def _commit_failures(self) -> int:
+        return self._ledger.failures
 
     def participating_rank(self) -> Optional[int]:
         """This replica's rank among the participants (None if not participating). Blocks on the quorum."""
         if self._quorum_future is None:
             return None
         self.wait_quorum()
-        return self._participating_replica_rank
+        return self._participation.rank
 
     def num_participants(self) -> int:
         """Number of replicas contributing to this step. Blocks on the quorum."""
         if self._quorum_future is None:
             return 0
         self.wait_quorum()
-        assert self._participating_replica_world_size >= 0, "internal error"
-        return self._participating_replica_world_size
+        assert self._participation.world >= 0, "internal error"
+        return self._participation.world
 
     def is_participating(self) -> bool:
-        if self._participating_replica_rank is None:
+        if self._participation.rank is None:
             return False
         if self._healing:
             assert self._use_async_quorum
             return False
         return True
 
+    # reference attribute names, for code that pokes at them
+    @property
+    def _participating_replica_rank(self) -> Optional[int]:
+        return self._participation.rank
+
+    @property
+    def _participating_replica_world_size(self) -> int:
+        return self._participation.world
+
 
 class _ManagerLogger:
+    """``[replica/rank - step N]``-prefixed logging."""
+
     def __init__(self, manager: Manager, replica_id: str, group_rank: int) -> None:
         self._logger = logging.getLogger(__name__)
-        self._replica_id, self._group_rank, self._manager = replica_id, group_rank, manager
+        self._who = f"{replica_id}/{group_rank}"
+        self._manager = weakref.ref(manager)
 
-    def prefix(self) -> str:
-        return f"[{self._replica_id}/{self._group_rank} - step {self._manager.current_step()}]"
+    def _fmt(self, msg: str) -> str:
+        m = self._manager()
+        return f"[{self._who} - step {m._ledger.step if m is not None else '?'}] {msg}"
 
     def info(self, msg: str) -> None:
-        self._logger.info(f"{self.prefix()} {msg}")
+        self._logger.info(self._fmt(msg))
 
     def warn(self, msg: str) -> None:
-        self._logger.warning(f"{self.prefix()} {msg}")
+        self._logger.warning(self._fmt(msg))
 
     def exception(self, msg: str) -> None:
-        self._logger.exception(f"{self.prefix()} {msg}")
+        self._logger.exception(self._fmt(msg))
 
 
 # ------------------------------------------------------------------ managed work

@@ -189,7 +189,8 @@ class FlatParams:
     ALIGN = 128  # elements; keeps every view 256 B aligned
 
     def __init__(self, module: nn.Module, grad_alloc: Optional[Callable[[int], torch.Tensor]] = None,
-                 device: Optional[torch.device] = None) -> None:
+                 device: Optional[torch.device] = None,
+                 param_alloc: Optional[Callable[[int], torch.Tensor]] = None) -> None:
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         assert named, "module has no parameters"
         dev, dt = named[0][1].device, named[0][1].dtype
@@ -216,7 +217,10 @@ class FlatParams:
             offs.append(total)
             total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = total
-        self.param = torch.zeros(total, dtype=dt, device=dev)
+        # ``param_alloc`` places the weights in peer-visible memory too (FT-ZeRO-1: the holder of a slice stores
+        # the updated bf16 weights straight into every replica's parameter buffer)
+        self.param = param_alloc(total)[:total] if param_alloc is not None else torch.zeros(total, dtype=dt, device=dev)
+        assert self.param.numel() == total and self.param.dtype == dt
         self.grad = grad_alloc(total) if grad_alloc is not None else torch.zeros(total, dtype=dt, device=dev)
         assert self.grad.numel() >= total and self.grad.dtype == dt
         self.grad = self.grad[:total]
@@ -261,6 +265,16 @@ class FlatParams:
         elif g.data_ptr() != slot.data_ptr():
             slot.copy_(g)
         p.grad = slot
+
+    def buckets_from_ranges(self, ranges) -> List[Tuple[int, int, List[nn.Parameter]]]:
+        """(start, end, params) for caller-chosen element ranges (each parameter must fall inside exactly one)."""
+        out: List[Tuple[int, int, List[nn.Parameter]]] = []
+        for lo, hi in ranges:
+            ps = [p for p, o in zip(self.params, self.offsets) if lo <= o < hi]
+            assert all(o + p.numel() <= hi for p, o in zip(self.params, self.offsets) if lo <= o < hi), "parameter straddles a range"
+            out.append((int(lo), int(hi), ps))
+        assert sum(len(b[2]) for b in out) == len(self.params), "ranges must cover every parameter exactly once"
+        return out
 
     def buckets(self, bucket_elems: int) -> List[Tuple[int, int, List[nn.Parameter]]]:
         """Contiguous (start, end, params) buckets in gradient-production order."""

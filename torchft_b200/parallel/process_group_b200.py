@@ -96,6 +96,11 @@ class ProcessGroupB200(ProcessGroup):
         device: CUDA device of this rank (default: current device).
     """
 
+    # every member maps every other member's memory: the group is confined to one NVSwitch domain / host,
+    # so the Manager may default to the NVLink heal transport and to liveness-driven aborts
+    single_host = True
+    supports_liveness_abort = True
+
     def __init__(self, timeout: timedelta = timedelta(seconds=60), staging_bytes: Optional[int] = None,
                  device: Optional[torch.device] = None) -> None:
         super().__init__(0, 1)
@@ -112,14 +117,22 @@ class ProcessGroupB200(ProcessGroup):
         self._sidecar: Optional[ProcessGroup] = None
         self._sidecar_lock = threading.Lock()
         self._aborted: Optional[Exception] = None
+        self._configure_hooks: List[Any] = []
 
     # ------------------------------------------------------------- lifecycle
+    def add_configure_hook(self, fn: Any) -> None:
+        """``fn(store, rank, world, quorum_id)`` runs at the end of every :meth:`configure` with the quorum-scoped
+        store, after the peer map is in place (used by the FT-ZeRO-1 optimizer to re-shard its state)."""
+        self._configure_hooks.append(fn)
+
     def configure(self, store_addr: str, replica_id: str, rank: int, world_size: int, quorum_id: Optional[int] = None,
                   group_rank: Optional[int] = None, group_world_size: Optional[int] = None,
                   global_ranks: Optional[List[int]] = None) -> None:
         with torch.cuda.device(self._device):
             store = create_store_client(store_addr, self._timeout)
             self._comm.configure(PrefixStore("b200", store), rank, world_size, int(quorum_id or 0))
+            for hook in self._configure_hooks:
+                hook(PrefixStore("b200hook", store), rank, world_size, int(quorum_id or 0))
         self._rank, self._world = rank, world_size
         self._store_addr = store_addr
         self._cfg = (replica_id, rank, world_size, quorum_id, group_rank, group_world_size, global_ranks)

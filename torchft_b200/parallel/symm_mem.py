@@ -20,6 +20,7 @@ the analogue of ``ncclCommAbort`` without tearing anything down.
 from __future__ import annotations
 
 import json
+import logging
 import os
 import socket
 import threading
@@ -31,6 +32,8 @@ from typing import Any, Dict, List, Optional, Tuple
 import torch
 
 from torchft_b200.ops import _native
+
+logger = logging.getLogger(__name__)
 
 _CH_ALLREDUCE = 0
 _CH_Q8 = 1
@@ -116,6 +119,8 @@ class SymmetricComm:
         self._barrier_mode = int(os.environ.get("TORCHFT_B200_BARRIER_MODE", "2"))
         self._force_plan: Optional[Tuple[int, int]] = None  # (algo, blocks) override for tuning sweeps
         self.launches = 0  # native kernel launches issued (bench reports this)
+        self._ptrs: Dict[str, List[int]] = {}  # segment -> mapped base pointer per quorum rank
+        self._commit_seq = 0
         self._hostname = socket.gethostname()
 
     # ------------------------------------------------------------------ memory
@@ -246,22 +251,62 @@ class SymmetricComm:
                     if vkey not in needed_vmm:
                         K.vmm_unmap(va, size, h)  # our reference kept the memory alive even if the peer died
                 self._peer_vmm = needed_vmm
-                core_ptrs = ptrs["core"]
-                pads = core_ptrs  # signal pad sits at offset 0 of the core segment
-                self._tables = {}
-                base = K.PeerTable([p + self._pad_bytes for p in core_ptrs], pads, rank, world)
-                base.set_timeout_ms(self._timeout.total_seconds() * 1e3)
-                self._tables["core"] = base
-                for n in names:
-                    if n != "core":
-                        self._tables[n] = base.with_data(ptrs[n])
-                floor = max(int(d["floor"]) for d in descs)
-                self._flag = max(floor, int(epoch) << 32) + 16
-                self._rank, self._world, self._epoch = rank, world, int(epoch)
-                self._nvls_min = self._nvls_min_env if self._nvls_min_env is not None else self._default_nvls_min(world)
+                self._install(ptrs, rank, world, int(epoch), max(int(d["floor"]) for d in descs))
                 if self._mode == "vmm" and self._nvls_enabled and world > 1 and K.multicast_supported():
                     self._setup_multicast(store, descs, [n for n in names if n != "core"], rank, world)
                 self._configured = True
+
+    def _install(self, ptrs: Dict[str, List[int]], rank: int, world: int, epoch: int, floor: int) -> None:
+        """Build the per-segment peer tables from mapped base pointers and restart the flag sequence."""
+        K = self._K
+        self._ptrs = ptrs
+        core_ptrs = ptrs["core"]
+        pads = core_ptrs  # signal pad sits at offset 0 of the core segment
+        self._tables = {}
+        base = K.PeerTable([p + self._pad_bytes for p in core_ptrs], pads, rank, world)
+        base.set_timeout_ms(self._timeout.total_seconds() * 1e3)
+        self._tables["core"] = base
+        for n in ptrs:
+            if n != "core":
+                self._tables[n] = base.with_data(ptrs[n])
+        self._flag = max(floor, int(epoch) << 32) + 16
+        self._rank, self._world, self._epoch = rank, world, int(epoch)
+        self._nvls_min = self._nvls_min_env if self._nvls_min_env is not None else self._default_nvls_min(world)
+
+    @staticmethod
+    def virtual_world(world: int, segments: Dict[str, int], device: Optional[torch.device] = None,
+                      presignal: bool = True, timeout: timedelta = timedelta(seconds=10),
+                      staging_bytes: int = 8 << 20) -> "List[SymmetricComm]":
+        """``world`` ranks of ONE quorum inside this process, all on ``device`` (testing / self-check harness).
+
+        Every rank gets its own segments and signal pad; the peer tables point at each other directly (no IPC).
+        With ``presignal`` every flag slot is pre-set to "arrived", so a rank's kernel never waits: because each
+        collective only ever reads slice r of all buffers and writes slice r back (or, one-shot, writes nothing
+        shared), running rank 0's kernel, then rank 1's, ... reproduces the W-rank result exactly -- in one
+        process, one kernel at a time, which is what profilers (ncu serialises launches), compute-sanitizer and
+        the one-GPU test tier need. With ``presignal=False`` the ranks synchronise for real and must be launched
+        concurrently on different streams.
+        """
+        comms = [SymmetricComm(device, staging_bytes=staging_bytes, timeout=timeout) for _ in range(world)]
+        for c in comms:
+            c._mode = "ipc"
+            c._ensure_core()
+            for name, nbytes in segments.items():
+                c._alloc_segment(name, nbytes)
+        names = list(comms[0]._segments)
+        ptrs = {n: [c._segments[n].ptr for c in comms] for n in names}
+        for r, c in enumerate(comms):
+            c._install({n: list(v) for n, v in ptrs.items()}, r, world, epoch=1, floor=0)
+            c._configured = True
+            if presignal:
+                pad = c._segments["core"].tensor[: c._K.SIGNAL_PAD_BYTES].view(torch.int64)
+                pad.fill_((1 << 62) | 1)  # ">= any flag" and "verdict ok" at once
+        torch.cuda.synchronize(comms[0].device)
+        return comms
+
+    def segment(self, name: str) -> torch.Tensor:
+        """uint8 view of this rank's segment ``name``."""
+        return self._segments[name].tensor
 
     # --------------------------------------------------------------- multicast
     def _store_barrier(self, store: Any, key: str, world: int) -> None:
@@ -434,6 +479,67 @@ class SymmetricComm:
                                scale, self._next_flag(), _CH_Q8, contribute, blocks, self._barrier_mode, sp)
                 self.launches += 1
 
+    # ------------------------------------------------------------------ FT-ZeRO-1 (csrc/kernels/zero1.cu)
+    def peer_pointers(self, name: str) -> List[int]:
+        """Mapped base address of segment ``name`` on every quorum rank (index = rank)."""
+        return list(self._ptrs[name])
+
+    def _mc_base(self, name: str, nbytes: int) -> int:
+        mc = self._mc.get(name)
+        return mc[1] if (mc is not None and self._world > 1 and nbytes >= self._nvls_min) else 0
+
+    def zero1_reduce_scatter_(self, segment: str, off: int, nelem: int, scale: float, contribute: bool,
+                              replication: int, blocks: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Reduce-scatter ``nelem`` bf16 elements at byte offset ``off`` of ``segment`` in place: afterwards rank r
+        (and its ``replication - 1`` successors) hold the scaled sum of slice r."""
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            blocks = max(1, min(blocks, self._K.MAX_BLOCKS, max(1, (nelem * 2) // (64 << 10))))
+            self._K.zero1_reduce_scatter(self._tables[segment], self._status, self._mc_base(segment, nelem * 2), off, nelem,
+                                         scale, self._next_flag(), _CH_ALLREDUCE, contribute, replication, blocks,
+                                         self._threads, self._barrier_mode, _native.stream_ptr(stream))
+            self.launches += 1
+
+    def zero1_commit_(self, gate: torch.Tensor, host_ok: bool, exchange: bool,
+                      stream: Optional[torch.cuda.Stream] = None) -> int:
+        """Device-side commit verdict (AND over the quorum when ``exchange``): writes ``gate[0]`` (verdict),
+        increments ``gate[1]`` on success and posts the verdict to the host-mapped ring. Returns the sequence
+        number to pass to :meth:`verdict`."""
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            self._commit_seq = (self._commit_seq + 1) & 0x3fffffff
+            seq = self._commit_seq
+            self._K.zero1_commit(self._tables["core"], self._status, gate.data_ptr(), self._next_flag(), seq, _CH_USER,
+                                 bool(host_ok), bool(exchange), _native.stream_ptr(stream))
+            self.launches += 1
+            return seq
+
+    def verdict(self, seq: int) -> Optional[bool]:
+        """Verdict of commit ``seq`` if the kernel has run, else ``None`` (never blocks)."""
+        v = self._status.verdict(seq)
+        return None if v < 0 else bool(v)
+
+    def zero1_update_(self, segment: str, poff: int, grad: int, master: int, m: int, v: int, nelem: int,
+                      hyper: Tuple[float, float, float, float, float], gate: torch.Tensor, replication: int, mode: int,
+                      blocks: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Gated AdamW on the held slices of one unit + all-gather of the primary slice's new bf16 weights into
+        ``segment`` on every rank (``mode`` 1: ungated re-broadcast of bf16(master), no state change)."""
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            lr, b1, b2, eps, wd = hyper
+            if self._world == 1:
+                blocks = max(1, min(148 * 16, (nelem // 8 + 511) // 512))
+            else:
+                blocks = max(1, min(blocks, self._K.MAX_BLOCKS, max(1, (nelem * 2) // (64 << 10))))
+            self._K.zero1_adamw_allgather(self._tables[segment], self._status, self._mc_base(segment, nelem * 2),
+                                          gate.data_ptr(), poff, grad, master, m, v, nelem, lr, b1, b2, eps, wd,
+                                          self._next_flag(), _CH_HEAL, replication, mode, blocks, self._threads,
+                                          self._barrier_mode, _native.stream_ptr(stream))
+            self.launches += 1
+
     # ------------------------------------------------------------------ status
     def abort(self) -> None:
         """Make every in-flight / future kernel wait bail out immediately."""
@@ -487,3 +593,21 @@ class SymmetricComm:
             self._configured = False
             # local segments are intentionally leaked until process exit if a
             # peer may still have them mapped; free only the python views
+
+    def free_segments(self) -> None:
+        """Return this rank's segments to the driver. Only after :meth:`shutdown` AND once every peer has shut down
+        too (they unmap on shutdown): a benchmark that builds a second trainer in the same process needs the memory."""
+        with self._lock:
+            assert not self._configured, "shutdown() first"
+            torch.cuda.synchronize(self.device)
+            for seg in self._segments.values():
+                seg.tensor = torch.empty(0, dtype=torch.uint8)
+                try:
+                    if self._mode == "vmm":
+                        self._K.vmm_unmap(seg.ptr, seg.nbytes, seg.mem_handle)
+                    else:
+                        self._K.symm_free(seg.ptr)
+                except Exception:  # noqa: BLE001
+                    logger.warning("could not free symmetric segment %s", seg.name)
+            self._segments = {}
+            self._status = None

@@ -1,17 +1,25 @@
 """High-level fault-tolerant trainer: the "one call a user makes" per step.
 
-Wires together, B200-first:
+Two pipelines over the same model code (``models/llama.py``):
 
-    ProcessGroupB200 (NVLink peer-memory collectives, remap-on-quorum)
-      -> Manager (quorum / heal / commit protocol; C++ control plane)
-      -> FlatParams (one flat bf16 parameter buffer, one flat SYMMETRIC gradient buffer)
-      -> FlatDistributedDataParallel (per-bucket fused all-reduce overlapped with backward)
-      -> OptimizerWrapper(FlatAdamW) (single-launch AdamW, stepped only on commit)
+``backend="b200"`` (default) -- FT-ZeRO-1 on the NVLink data plane (``parallel/zero1.py``)::
 
-This is the HSDP configuration of BASELINE.json with shard degree 1: every GPU is
-one replica group holding the full model (180 GB of HBM3e fits Llama-3-8B weights,
-gradients, fp32 master weights and Adam state), and fault tolerance lives on the
-replicated dimension exactly as in the reference (README.md:37-42).
+    ProcessGroupB200 (peer-memory kernels, remap-on-quorum)
+      -> Manager (quorum / heal on the C++ control plane; commit verdict ON THE DEVICE)
+      -> FlatParams: weights + gradients in flat SYMMETRIC bf16 buffers
+      -> backward: per-block reduce-scatter kernel (1/N scale, zero contribution, buddy push) on the comm stream
+      -> commit:   one verdict kernel (AND over the quorum through the signal pads), no host sync, no RPC
+      -> update:   gated AdamW on the held slices fused with the all-gather of the new weights, block by
+                   block on the optimizer stream while the next forward already runs
+
+``backend="nccl"`` -- the reference-equivalent arm: stock ``ProcessGroupNCCL`` re-created per quorum,
+per-bucket all-reduce SUM then ``/N``, host-synchronous ``should_commit`` RPC, full AdamW on every
+replica (/root/reference/torchft/manager.py:466-478,884-903, /root/reference/torchft/optim.py:52-55).
+``backend="b200"`` with ``zero1=False`` runs that same classic structure on the native all-reduce kernels.
+
+This is the HSDP configuration of BASELINE.json with shard degree 1: every GPU is one replica group holding
+the full bf16 model (180 GB of HBM3e), and the replicated dimension is both the fault-tolerance dimension
+(README.md:37-42 of the reference) and -- new here -- the dimension the optimizer is partitioned over.
 """
 
 from __future__ import annotations
@@ -19,10 +27,9 @@ from __future__ import annotations
 import dataclasses
 import os
 from datetime import timedelta
-from typing import Any, Dict, Optional
+from typing import Any, Dict, List, Optional, Tuple
 
 import torch
-from torch import nn
 from torch.distributed import TCPStore
 
 from torchft_b200.ddp import FlatDistributedDataParallel
@@ -41,11 +48,12 @@ class FaultTolerantTrainer:
         replica_id: this replica group's name (``"replica_3"``); trailing digits give its global rank
         min_replica_size: minimum participating replicas for a step to commit
         backend: ``"b200"`` (native peer-memory kernels) or ``"nccl"`` (reference-equivalent baseline)
-        bucket_mb: gradient bucket size for the overlapped all-reduce
-        should_quantize: fused fp8 gradient all-reduce
-        overlap_optimizer: run AdamW layer by layer on a side stream so the next forward starts as soon
-            as its first layers are updated (default: env ``TORCHFT_B200_OVERLAP_OPT``, else on)
-        optimizer_blocks: CTA cap of the overlapped AdamW launches (0 = kernel default)
+        zero1: partition the optimizer over the replicas and commit on the device (default for ``b200``;
+            env ``TORCHFT_B200_ZERO1=0`` turns it off)
+        replication: holders per slice of optimizer state (``k`` of FT-ZeRO-1)
+        bucket_mb: gradient bucket size for the classic (all-reduce) pipeline
+        should_quantize: fused fp8 gradient all-reduce (classic pipeline)
+        overlap_optimizer: classic pipeline: run AdamW stage by stage on a side stream under the next forward
     """
 
     def __init__(self, model: str | LlamaConfig, lighthouse_addr: str, replica_id: str = "replica_0",
@@ -54,7 +62,7 @@ class FaultTolerantTrainer:
                  timeout: timedelta = timedelta(seconds=60), device: Optional[torch.device] = None,
                  activation_checkpoint: Optional[str] = None, init_sync: bool = False,
                  use_async_quorum: bool = True, overlap_optimizer: Optional[bool] = None,
-                 optimizer_blocks: int = 0) -> None:
+                 optimizer_blocks: int = 0, zero1: Optional[bool] = None, replication: int = 2) -> None:
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         torch.cuda.set_device(self.device)
         cfg = CONFIGS[model] if isinstance(model, str) else model
@@ -62,6 +70,11 @@ class FaultTolerantTrainer:
             cfg = dataclasses.replace(cfg, activation_checkpoint=activation_checkpoint)
         self.cfg = cfg
         self.backend = backend
+        if zero1 is None:
+            zero1 = backend == "b200" and os.environ.get("TORCHFT_B200_ZERO1", "1") != "0" and not should_quantize
+        if zero1 and backend != "b200":
+            raise ValueError("zero1 needs the b200 backend")
+        self.zero1 = bool(zero1)
 
         # the replica group's own store (group world size 1 => this process hosts it)
         self._store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
@@ -79,16 +92,29 @@ class FaultTolerantTrainer:
 
         # build on meta, materialise directly into the flat buffers, then initialise in place
         self.model = Llama(cfg, device="meta")
-        numel_bytes = sum((p.numel() + FlatParams.ALIGN - 1) // FlatParams.ALIGN * FlatParams.ALIGN
-                          for p in self.model.parameters()) * 2
-        if backend == "b200":
-            grad_alloc = lambda n: self.pg.alloc_symmetric("grads", numel_bytes).view(torch.bfloat16)  # noqa: E731
+        numel = sum((p.numel() + FlatParams.ALIGN - 1) // FlatParams.ALIGN * FlatParams.ALIGN for p in self.model.parameters())
+        self.zopt: Any = None
+        if self.zero1:
+            from torchft_b200.parallel.zero1 import Zero1Optimizer
+
+            # the optimizer owns the five symmetric flat buffers; FlatParams adopts two of them. Units (= gradient
+            # buckets = update launches) are the forward stages, known once the parameters have offsets.
+            self.zopt = Zero1Optimizer(self.pg, numel, lr=lr, replication=replication, blocks=optimizer_blocks or None)
+            self.flat = FlatParams(self.model, grad_alloc=lambda n: self.zopt.grad, device=self.device,
+                                   param_alloc=lambda n: self.zopt.param)
         else:
-            grad_alloc = None
-        self.flat = FlatParams(self.model, grad_alloc=grad_alloc, device=self.device)
+            grad_alloc = (lambda n: self.pg.alloc_symmetric("grads", numel * 2).view(torch.bfloat16)) if backend == "b200" else None
+            self.flat = FlatParams(self.model, grad_alloc=grad_alloc, device=self.device)
         self.model.init_weights(seed)
-        self.inner_optim = FlatAdamW(self.flat.param, self.flat.grad, lr=lr)
-        self.inner_optim.direct_grads = True  # step_device() drops p.grad; wgrad GEMMs fill the flat buffer
+        self._stage_ranges = self._compute_stage_ranges()
+
+        if self.zero1:
+            self.zopt.set_units(self._stage_ranges)
+            self.zopt.seed_master()
+            self.inner_optim: Any = self.zopt
+        else:
+            self.inner_optim = FlatAdamW(self.flat.param, self.flat.grad, lr=lr)
+            self.inner_optim.direct_grads = True  # step_device() drops p.grad; wgrad GEMMs fill the flat buffer
 
         self.manager = Manager(
             pg=self.pg,
@@ -107,26 +133,33 @@ class FaultTolerantTrainer:
             replica_id=replica_id,
             init_sync=init_sync,
         )
-        self.ddp = FlatDistributedDataParallel(self.manager, self.model, self.flat, bucket_mb=bucket_mb,
-                                               should_quantize=should_quantize)
-        self.optim = OptimizerWrapper(self.manager, self.inner_optim)
-        if overlap_optimizer is None:
-            overlap_optimizer = os.environ.get("TORCHFT_B200_OVERLAP_OPT", "1") != "0"
-        self._opt_blocks = int(os.environ.get("TORCHFT_B200_OPT_BLOCKS", optimizer_blocks))
         self._opt_stream: Optional[torch.cuda.Stream] = None
-        if overlap_optimizer:
-            self._setup_optimizer_overlap()
+        self._opt_pending = False
+        if self.zero1:
+            self.ddp = FlatDistributedDataParallel(self.manager, self.model, self.flat,
+                                                   bucket_ranges=sorted(self._stage_ranges), reduce_fn=self._reduce_unit)
+            self._bucket_unit = {bi: self._stage_ranges.index((lo, hi))
+                                 for bi, (lo, hi) in enumerate(sorted(self._stage_ranges))}
+            self._setup_stage_gates()
+            self.zopt.bind_stream(self._opt_stream)
+            self.optim: Any = None
+        else:
+            self.ddp = FlatDistributedDataParallel(self.manager, self.model, self.flat, bucket_mb=bucket_mb,
+                                                   should_quantize=should_quantize)
+            self.optim = OptimizerWrapper(self.manager, self.inner_optim)
+            if overlap_optimizer is None:
+                overlap_optimizer = os.environ.get("TORCHFT_B200_OVERLAP_OPT", "1") != "0"
+            self._opt_blocks = int(os.environ.get("TORCHFT_B200_OPT_BLOCKS", optimizer_blocks))
+            if overlap_optimizer:
+                self._setup_stage_gates()
         self._tok: Optional[torch.Tensor] = None
         self._tgt: Optional[torch.Tensor] = None
+        self._loss_host: Optional[torch.Tensor] = None
+        self._loss_event: Optional[torch.cuda.Event] = None
 
-    # ------------------------------------------------- optimizer / forward overlap
-    def _setup_optimizer_overlap(self) -> None:
-        """Cut the flat AdamW update into one range per top-level module, in FORWARD order.
-
-        The update is HBM-bound and the forward is tensor-core-bound, so instead of idling the tensor
-        cores for the whole update (12 % of a Llama-3-8B step) the ranges run on a side stream and each
-        module's forward only waits for the event of the range(s) holding its own parameters.
-        """
+    # ------------------------------------------------- stages: optimizer units == forward gates
+    def _compute_stage_ranges(self) -> List[Tuple[int, int]]:
+        """Element range of the flat buffer per top-level module, in FORWARD order; the ranges tile the buffer."""
         where = {id(p): (o, p.numel()) for p, o in zip(self.flat.params, self.flat.offsets)}
         ranges = []
         for stage in self.model.param_stages():
@@ -137,10 +170,15 @@ class FaultTolerantTrainer:
         covered = sorted(ranges)
         assert covered[0][0] == 0 and covered[-1][1] == self.flat.numel and all(
             a[1] == b[0] for a, b in zip(covered, covered[1:])), "parameter stages must tile the flat buffer"
-        self._opt_ranges = ranges
-        self._opt_events = [torch.cuda.Event() for _ in ranges]
+        return ranges
+
+    def _setup_stage_gates(self) -> None:
+        """The update of stage ``i`` runs on a side stream and records ``events[i]``; the NEXT forward of stage ``i``
+        waits for exactly that event. The update is HBM/NVLink-bound and the forward tensor-core-bound, so they
+        overlap instead of idling the tensor cores for the whole update."""
+        self._opt_ranges = self._stage_ranges
+        self._opt_events = [torch.cuda.Event() for _ in self._stage_ranges]
         self._opt_stream = torch.cuda.Stream(device=self.device)
-        self._opt_pending = False
 
         def gate(stage: int) -> None:
             if self._opt_pending:
@@ -148,6 +186,13 @@ class FaultTolerantTrainer:
 
         self.model.stage_hook = gate
 
+    # ------------------------------------------------- FT-ZeRO-1 pipeline pieces
+    def _reduce_unit(self, bucket: int, start: int, end: int) -> Any:
+        m = self.manager
+        unit = self._bucket_unit[bucket]
+        return m.guarded(lambda: self.zopt.reduce_scatter(unit, 1.0 / max(m.num_participants(), 1), m.is_participating()))
+
+    # ------------------------------------------------- classic pipeline pieces
     def _optimizer_step(self) -> None:
         if self._opt_stream is None:
             self.inner_optim.step()
@@ -161,16 +206,26 @@ class FaultTolerantTrainer:
         if self._opt_stream is not None and self._opt_pending:
             torch.cuda.current_stream().wait_stream(self._opt_stream)
 
+    def join(self) -> None:
+        """Order the current stream behind everything the last step enqueued on side streams (the optimizer
+        update / weight all-gather), e.g. before recording a timing event or reading the weights."""
+        self._join_optimizer()
+
     # -------------------------------------------------------------- heal hooks
     def state_dict(self) -> Dict[str, Any]:
         if self._opt_stream is not None:
             self._opt_stream.synchronize()  # heal senders read on their own stream: hand them a finished update
+        if self.zero1:
+            return self.zopt.state_dict()
         o = self.inner_optim
         return {"param": self.flat.param, "master": o.master, "m": o.m, "v": o.v, "t": o.t}
 
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
-        o = self.inner_optim
         self._join_optimizer()
+        if self.zero1:
+            self.zopt.load_state_dict(sd)
+            return
+        o = self.inner_optim
         with torch.no_grad():
             for name, dst in (("param", self.flat.param), ("master", o.master), ("m", o.m), ("v", o.v)):
                 if sd[name].data_ptr() != dst.data_ptr():
@@ -180,6 +235,16 @@ class FaultTolerantTrainer:
     # -------------------------------------------------------------------- step
     def step_device(self, tokens: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         """One fault-tolerant optimisation step on device-resident inputs; returns the loss tensor (device)."""
+        if self.zero1:
+            self.manager.start_quorum()       # async; its thread first books the previous step's device verdict
+            self.flat.reset_grads()           # wgrad GEMMs write the flat gradient buffer directly: no memset
+            loss = self.ddp(tokens, targets)  # forward; stage i waits for the event of unit i's update
+            loss.backward()                   # per-unit reduce-scatter kernels launch from the grad hooks
+            self.ddp.finish(wait=False)       # issue what is left; the optimizer stream orders itself behind them
+            self.manager.commit_on_device(self.zopt)  # verdict kernel (no host sync, no RPC in steady state)
+            self.zopt.update(self._opt_events)        # gated AdamW + weight all-gather, unit by unit
+            self._opt_pending = True
+            return loss
         self.optim.zero_grad(set_to_none=True)  # start_quorum (async); no memset:
         self.flat.reset_grads()                  # wgrad GEMMs write the flat gradient buffer directly
         loss = self.ddp(tokens, targets)  # forward (fused kernels + cuBLAS + SDPA)
@@ -189,8 +254,7 @@ class FaultTolerantTrainer:
             self._optimizer_step()        # cut per layer so the next forward overlaps it
         return loss
 
-    def step(self, tokens_cpu: torch.Tensor, targets_cpu: torch.Tensor) -> float:
-        """End-to-end step: pinned-host inputs -> H2D -> train step -> D2H loss."""
+    def _stage_inputs(self, tokens_cpu: torch.Tensor, targets_cpu: torch.Tensor) -> None:
         B, S = tokens_cpu.shape
         if self._tok is None or self._tok.shape != tokens_cpu.shape:
             self._tok = torch.empty((B, S), dtype=torch.int64, device=self.device)
@@ -198,8 +262,39 @@ class FaultTolerantTrainer:
         assert self._tgt is not None
         self._tok.copy_(tokens_cpu, non_blocking=True)
         self._tgt.copy_(targets_cpu, non_blocking=True)
+
+    def step(self, tokens_cpu: torch.Tensor, targets_cpu: torch.Tensor) -> float:
+        """End-to-end step: pinned-host inputs -> H2D -> train step -> D2H loss (blocks until the loss is on the host)."""
+        self._stage_inputs(tokens_cpu, targets_cpu)
         loss = self.step_device(self._tok, self._tgt)
         return float(loss.item())
+
+    def step_async(self, tokens_cpu: torch.Tensor, targets_cpu: torch.Tensor) -> Optional[float]:
+        """Like :meth:`step`, but the loss comes back one step late: this call enqueues the step and the D2H copy
+        of ITS loss into pinned memory, and returns the PREVIOUS step's loss (``None`` on the first call). The host
+        never waits for the step it just launched, so the GPU queue stays full; every step still performs its
+        H2D input copy and its D2H loss read."""
+        prev: Optional[float] = None
+        if self._loss_event is not None:
+            self._loss_event.synchronize()
+            assert self._loss_host is not None
+            prev = float(self._loss_host[0])
+        self._stage_inputs(tokens_cpu, targets_cpu)
+        loss = self.step_device(self._tok, self._tgt)
+        if self._loss_host is None:
+            self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+            self._loss_event = torch.cuda.Event()
+        self._loss_host.copy_(loss.detach().float().reshape(1), non_blocking=True)
+        self._loss_event.record()
+        return prev
+
+    def last_loss(self) -> Optional[float]:
+        """Loss of the most recent :meth:`step_async` (waits for it)."""
+        if self._loss_event is None:
+            return None
+        self._loss_event.synchronize()
+        assert self._loss_host is not None
+        return float(self._loss_host[0])
 
     def shutdown(self) -> None:
         if self._opt_stream is not None:
