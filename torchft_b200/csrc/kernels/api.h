@@ -37,6 +37,18 @@ void zero1_adamw_allgather_launch(const PeerTable& pt, StatusBlock* st, void* mc
                                   int replication, int mode, int blocks, int threads, int barrier_mode,
                                   cudaStream_t stream);
 
+// collectives.cu --------------------------------------------------------------
+// push exchange = all-gather / broadcast / all-to-all over staging slots (arrays have pt.world entries);
+// reduce-scatter; point-to-point pieces through per-pair mailboxes.
+void push_exchange_launch(const PeerTable& pt, StatusBlock* st, const void* in, void* out, const size_t* send_off,
+                          const size_t* send_len, const size_t* recv_len, const size_t* out_off, size_t slot_stride,
+                          uint64_t flag, int channel, int blocks, int barrier_mode, cudaStream_t stream);
+void reduce_scatter_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* user_in, void* out, size_t n,
+                           int dtype, int op, float scale, uint64_t flag, int channel, int blocks, int barrier_mode,
+                           cudaStream_t stream);
+void p2p_launch(const PeerTable& pt, StatusBlock* st, int is_send, void* buf, size_t nbytes, int peer, size_t mailbox_off,
+                size_t mailbox_bytes, uint64_t seq0, int channel, cudaStream_t stream);
+
 // quant.cu -------------------------------------------------------------------
 size_t q8_ngroups(size_t nelem, int world);
 size_t q8_buffer_bytes(size_t nelem, int world);
@@ -56,6 +68,11 @@ void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const
                          const void* in_b, void* out, size_t nelem, int dtype, float post_scale,
                          uint64_t flag, int channel, int contribute, int blocks, int barrier_mode,
                          cudaStream_t stream);
+
+size_t q8_rs_buffer_bytes(size_t slice_elems, int world);
+void q8_reduce_scatter_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* in, void* out, size_t nelem,
+                              size_t slice_elems, int dtype, float post_scale, uint64_t flag, int channel,
+                              int contribute, int blocks, int barrier_mode, cudaStream_t stream);
 
 // model_ops.cu ---------------------------------------------------------------
 void rmsnorm_fwd_launch(const void* x, const void* w, void* y, float* rstd, int rows, int H,

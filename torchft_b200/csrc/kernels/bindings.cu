@@ -253,6 +253,40 @@ PYBIND11_MODULE(_K, m) {
       py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("flag"), py::arg("channel"), py::arg("replication"),
       py::arg("mode"), py::arg("blocks"), py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
 
+  m.def(
+      "push_exchange",
+      [](const PeerTableH& pt, const Status& st, uintptr_t in, uintptr_t out, const std::vector<size_t>& send_off,
+         const std::vector<size_t>& send_len, const std::vector<size_t>& recv_len, const std::vector<size_t>& out_off,
+         size_t slot_stride, uint64_t flag, int channel, int blocks, int barrier_mode, uintptr_t stream) {
+        const size_t w = (size_t)pt.pt.world;
+        if (send_off.size() != w || send_len.size() != w || recv_len.size() != w || out_off.size() != w)
+          throw std::runtime_error("push_exchange: need one entry per rank");
+        push_exchange_launch(pt.pt, st.dev(), P<void>(in), P<void>(out), send_off.data(), send_len.data(), recv_len.data(),
+                             out_off.data(), slot_stride, flag, channel, blocks, barrier_mode, S(stream));
+      },
+      py::arg("pt"), py::arg("status"), py::arg("input"), py::arg("output"), py::arg("send_off"), py::arg("send_len"),
+      py::arg("recv_len"), py::arg("out_off"), py::arg("slot_stride"), py::arg("flag"), py::arg("channel"),
+      py::arg("blocks"), py::arg("barrier_mode"), py::arg("stream"));
+  m.def(
+      "reduce_scatter",
+      [](const PeerTableH& pt, const Status& st, size_t off, uintptr_t user_in, uintptr_t out, size_t n, int dtype, int op,
+         float scale, uint64_t flag, int channel, int blocks, int barrier_mode, uintptr_t stream) {
+        reduce_scatter_launch(pt.pt, st.dev(), off, P<void>(user_in), P<void>(out), n, dtype, op, scale, flag, channel,
+                              blocks, barrier_mode, S(stream));
+      },
+      py::arg("pt"), py::arg("status"), py::arg("off"), py::arg("user_in"), py::arg("out"), py::arg("n"), py::arg("dtype"),
+      py::arg("op"), py::arg("scale"), py::arg("flag"), py::arg("channel"), py::arg("blocks"), py::arg("barrier_mode"),
+      py::arg("stream"));
+  m.def(
+      "p2p",
+      [](const PeerTableH& pt, const Status& st, bool is_send, uintptr_t buf, size_t nbytes, int peer, size_t mailbox_off,
+         size_t mailbox_bytes, uint64_t seq0, int channel, uintptr_t stream) {
+        p2p_launch(pt.pt, st.dev(), is_send ? 1 : 0, P<void>(buf), nbytes, peer, mailbox_off, mailbox_bytes, seq0, channel,
+                   S(stream));
+      },
+      py::arg("pt"), py::arg("status"), py::arg("is_send"), py::arg("buf"), py::arg("nbytes"), py::arg("peer"),
+      py::arg("mailbox_off"), py::arg("mailbox_bytes"), py::arg("seq0"), py::arg("channel"), py::arg("stream"));
+
   m.def("q8_ngroups", &q8_ngroups);
   m.def("q8_buffer_bytes", &q8_buffer_bytes);
   m.def("q8_quantize", [](uintptr_t a, uintptr_t b, size_t nelem, int dtype, int world, uintptr_t qbuf,
@@ -292,6 +326,19 @@ PYBIND11_MODULE(_K, m) {
       py::arg("pt"), py::arg("status"), py::arg("off"), py::arg("in_a"), py::arg("in_b"),
       py::arg("out"), py::arg("nelem"), py::arg("dtype"), py::arg("post_scale"), py::arg("flag"),
       py::arg("channel"), py::arg("contribute"), py::arg("blocks"), py::arg("barrier_mode"), py::arg("stream"));
+
+  m.def("q8_rs_buffer_bytes", &q8_rs_buffer_bytes);
+  m.def(
+      "q8_reduce_scatter",
+      [](const PeerTableH& pt, const Status& st, size_t off, uintptr_t in, uintptr_t out, size_t nelem, size_t slice_elems,
+         int dtype, float post_scale, uint64_t flag, int channel, bool contribute, int blocks, int barrier_mode,
+         uintptr_t stream) {
+        q8_reduce_scatter_launch(pt.pt, st.dev(), off, P<void>(in), P<void>(out), nelem, slice_elems, dtype, post_scale, flag,
+                                 channel, contribute ? 1 : 0, blocks, barrier_mode, S(stream));
+      },
+      py::arg("pt"), py::arg("status"), py::arg("off"), py::arg("input"), py::arg("out"), py::arg("nelem"),
+      py::arg("slice_elems"), py::arg("dtype"), py::arg("post_scale"), py::arg("flag"), py::arg("channel"),
+      py::arg("contribute"), py::arg("blocks"), py::arg("barrier_mode"), py::arg("stream"));
 
   m.def("rmsnorm_fwd", [](uintptr_t x, uintptr_t w, uintptr_t y, uintptr_t rstd, int rows, int H,
                           float eps, uintptr_t s) {

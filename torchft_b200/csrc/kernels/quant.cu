@@ -234,6 +234,12 @@ struct Q8Args {
   int channel;
   int contribute;
   int barrier_mode;
+  // mode 0: all-reduce (slices are contiguous runs of groups: slice_elems == groups_per_slice * 512).
+  // mode 1: reduce-scatter (torchft/collectives.py:159-294): rank-slice s covers elements
+  //         [s * slice_elems, (s+1) * slice_elems), quantised on its own group grid; `out` receives the
+  //         fp32-reduced, scaled slice of THIS rank directly (no requantise, no gather phase).
+  int mode;
+  size_t slice_elems;
 };
 
 template <typename T, int W>
@@ -250,13 +256,14 @@ __global__ void __launch_bounds__(512, 1) q8_allreduce_kernel(Q8Args a) {
     const size_t lo = s * slice + blockIdx.x * chunk;
     const size_t hi = min(lo + chunk, (s + 1) * slice);
     for (size_t g = lo + warp; g < hi; g += nwarp) {
-      const size_t e = g * kGroup + lane * 16;
+      const size_t e = (size_t)s * a.slice_elems + (g - (size_t)s * slice) * kGroup + lane * 16;
+      const size_t lim = min(a.nelem, (size_t)(s + 1) * a.slice_elems);
       float f[16];
       if (a.contribute) {
-        load16<T>(reinterpret_cast<const T*>(a.in_a), e, a.nelem, f);
+        load16<T>(reinterpret_cast<const T*>(a.in_a), e, lim, f);
         if (a.in_b != nullptr) {
           float h[16];
-          load16<T>(reinterpret_cast<const T*>(a.in_b), e, a.nelem, h);
+          load16<T>(reinterpret_cast<const T*>(a.in_b), e, lim, h);
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] -= h[i];
         }
@@ -303,6 +310,13 @@ __global__ void __launch_bounds__(512, 1) q8_allreduce_kernel(Q8Args a) {
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc[i] *= a.post_scale;
+      if (a.mode == 1) {
+        const size_t base = (size_t)rank * a.slice_elems;
+        const size_t valid = a.nelem > base ? min(a.slice_elems, a.nelem - base) : 0;
+        const size_t le = (g - (size_t)rank * slice) * kGroup + lane * 16;
+        if (le < valid) store16<T>(reinterpret_cast<T*>(a.out), le, valid, acc);
+        continue;
+      }
       Vec16 q;
       const float sc = group_quant(acc, &q);
 #pragma unroll
@@ -311,6 +325,11 @@ __global__ void __launch_bounds__(512, 1) q8_allreduce_kernel(Q8Args a) {
         st_stream(dst[p] + poff + g * kGroup + lane * 16, q);
       }
     }
+  }
+  if (a.mode == 1) {
+    // peers must not requantise their next message over staging we are still reading
+    block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/false, /*acquire=*/false, a.barrier_mode);
+    return;
   }
   if (!block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/true, /*acquire=*/true, a.barrier_mode)) return;
 
@@ -478,12 +497,52 @@ void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const
   a.channel = channel;
   a.contribute = contribute;
   a.barrier_mode = barrier_mode;
+  a.mode = 0;
+  a.slice_elems = a.ngroups / pt.world * kGroup;
   if (pt.world < 2) throw std::runtime_error("q8_allreduce: world must be >= 2");
   switch (dtype) {
     case kF32: q8_ar_w<float>(a, blocks, stream); break;
     case kBF16: q8_ar_w<__nv_bfloat16>(a, blocks, stream); break;
     case kF16: q8_ar_w<__half>(a, blocks, stream); break;
     default: throw std::runtime_error("q8_allreduce: unsupported dtype");
+  }
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+size_t q8_rs_buffer_bytes(size_t slice_elems, int world) {
+  const size_t g = (size_t)world * ((slice_elems + kGroup - 1) / kGroup);
+  return q8_payload_off(g) + g * kGroup;
+}
+
+void q8_reduce_scatter_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* in, void* out, size_t nelem,
+                              size_t slice_elems, int dtype, float post_scale, uint64_t flag, int channel,
+                              int contribute, int blocks, int barrier_mode, cudaStream_t stream) {
+  if (blocks < 1 || blocks > kMaxBlocks) throw std::runtime_error("q8_reduce_scatter: bad grid");
+  if (off & 15) throw std::runtime_error("q8_reduce_scatter: offset must be 16 B aligned");
+  if (pt.world < 2) throw std::runtime_error("q8_reduce_scatter: world must be >= 2");
+  const size_t es = dtype == kF32 ? 4 : 2;
+  if ((slice_elems * es) & 15) throw std::runtime_error("q8_reduce_scatter: rank slices must be 16 B aligned");
+  Q8Args a;
+  a.pt = pt;
+  a.st = st;
+  a.off = off;
+  a.in_a = in;
+  a.in_b = nullptr;
+  a.out = out;
+  a.nelem = nelem;
+  a.ngroups = (size_t)pt.world * ((slice_elems + kGroup - 1) / kGroup);
+  a.post_scale = post_scale;
+  a.flag = flag;
+  a.channel = channel;
+  a.contribute = contribute;
+  a.barrier_mode = barrier_mode;
+  a.mode = 1;
+  a.slice_elems = slice_elems;
+  switch (dtype) {
+    case kF32: q8_ar_w<float>(a, blocks, stream); break;
+    case kBF16: q8_ar_w<__nv_bfloat16>(a, blocks, stream); break;
+    case kF16: q8_ar_w<__half>(a, blocks, stream); break;
+    default: throw std::runtime_error("q8_reduce_scatter: unsupported dtype");
   }
   TFT_CUDA_CHECK(cudaGetLastError());
 }

@@ -6,18 +6,20 @@ gradient byte through NCCL (manager.py:466-468), this group
 
 * keeps CUDA context, streams, symmetric segments and signal pads alive across
   quorums and only *remaps peer handles* in ``configure`` (sub-millisecond);
-* runs all-reduce / broadcast / all-gather / reduce-scatter / barrier as ONE
-  hand-written sm_100a kernel each over NVLink peer memory (P2P loads + stores,
-  epoch-tagged flags, bounded abortable spins) on a dedicated comm stream, with
-  the 1/N scale, dtype handling and the non-participant zero contribution fused;
+* runs every collective as ONE hand-written sm_100a kernel over NVLink peer memory (P2P loads +
+  stores, epoch-tagged flags, bounded abortable spins) on a dedicated comm stream: all-reduce
+  (one-/two-shot, NVLS) with the 1/N scale, dtype handling and the non-participant zero
+  contribution fused; all-gather, broadcast and equal-split all-to-all as a push exchange through
+  staging slots; reduce-scatter; send / recv through per-pair mailboxes -- each moving exactly the
+  algorithmic bytes (``csrc/kernels/{allreduce,allreduce_nvls,collectives,quant,zero1}.cu``);
 * surfaces peer death as a latched ``errored()`` (kernel spin timeout / abort
   flag), the in-kernel analogue of ``ncclCommAbort``;
 * exposes ``alloc_symmetric`` so gradient buckets can live in peer-visible memory
   and be reduced with zero copies.
 
-Operations outside that set (send/recv, all-to-all, integer dtypes, CPU
-tensors) go to a lazily created NCCL/Gloo *sidecar* group over the same store,
-so the full c10d surface keeps working; nothing on the training hot path uses it.
+What the kernels cannot express (CPU tensors, non-contiguous views, integer reductions, all-to-all
+with unequal splits) goes to a lazily created NCCL *sidecar* group over the same store, so the
+full c10d surface keeps working; nothing on the training or heal paths uses it.
 """
 
 from __future__ import annotations
@@ -110,6 +112,8 @@ class ProcessGroupB200(ProcessGroup):
         self._device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._comm = SymmetricComm(self._device, staging_bytes=staging_bytes, timeout=timeout)
         self._stream = torch.cuda.Stream(device=self._device, priority=-1)
+        self._send_stream = torch.cuda.Stream(device=self._device, priority=-1)
+        self._recv_stream = torch.cuda.Stream(device=self._device, priority=-1)
         self._rank = 0
         self._world = 1
         self._store_addr: Optional[str] = None
@@ -209,8 +213,12 @@ class ProcessGroupB200(ProcessGroup):
         with torch.cuda.stream(self._stream):
             fn(self._stream)
             ev = self._stream.record_event()
-        for t in (result if isinstance(result, (list, tuple)) else [result]):
-            if isinstance(t, torch.Tensor):
+        stack = [result]
+        while stack:  # results may be nested lists (allgather)
+            t = stack.pop()
+            if isinstance(t, (list, tuple)):
+                stack.extend(t)
+            elif isinstance(t, torch.Tensor):
                 t.record_stream(self._stream)
         return StreamWork(ev, result)
 
@@ -252,92 +260,143 @@ class ProcessGroupB200(ProcessGroup):
     def allreduce_coalesced(self, tensors: List[torch.Tensor], opts: Any) -> Work:
         return self.allreduce(tensors, opts)
 
+    # Everything below is ONE push-exchange / reduce-scatter / p2p kernel per tensor (csrc/kernels/collectives.cu):
+    # algorithmic bytes over NVLink, no zero-padded all-reduce emulation, no NCCL. Only what the kernels cannot
+    # express (CPU tensors, non-contiguous views, integer reductions, unequal all-to-all splits) goes to the sidecar.
+    @staticmethod
+    def _raw_ok(t: torch.Tensor) -> bool:
+        return t.is_cuda and t.is_contiguous()
+
     def broadcast(self, tensor_list: List[torch.Tensor], opts: Any) -> Work:
         root = opts.rootRank
-        if all(self._native_ok(t) for t in tensor_list):
-            # broadcast == SUM where only the root contributes (others add zeros in-kernel)
+        if all(self._raw_ok(t) for t in tensor_list):
             def run(s: torch.cuda.Stream) -> None:
                 for t in tensor_list:
-                    self._comm.allreduce_(t, contribute=(self._rank == root), stream=s)
+                    self._comm.broadcast_(t, root, stream=s)
 
             return self._launch(run, tensor_list)
         return self._get_sidecar().broadcast(tensor_list, opts)
 
     def barrier(self, opts: Any = None) -> Work:
-        flag = torch.zeros(4, dtype=torch.float32, device=self._device)
-        return self._launch(lambda s: self._comm.allreduce_(flag, stream=s), None)
+        # a 16-byte all-reduce in the staging segment; the flag lives as long as the work (it used to be
+        # freed while the comm-stream kernel still read it)
+        with torch.cuda.stream(self._stream):
+            flag = torch.zeros(4, dtype=torch.float32, device=self._device)
+        return self._launch(lambda s: self._comm.allreduce_(flag, stream=s), flag)
 
     def allgather(self, output_tensors: List[List[torch.Tensor]], input_tensor: List[torch.Tensor], opts: Any) -> Work:
-        if all(self._native_ok(t) for t in input_tensor) and all(len(o) == self._world for o in output_tensors):
-            # gather == SUM over a buffer where rank r only fills slot r
+        if (all(self._raw_ok(t) for t in input_tensor) and all(len(o) == self._world for o in output_tensors)
+                and all(self._raw_ok(t) for o in output_tensors for t in o)):
             def run(s: torch.cuda.Stream) -> None:
                 for outs, inp in zip(output_tensors, input_tensor):
-                    n = inp.numel()
-                    pad = (n + 127) // 128 * 128
-                    buf = torch.zeros(self._world * pad, dtype=inp.dtype, device=inp.device)
-                    buf[self._rank * pad : self._rank * pad + n].copy_(inp.view(-1))
-                    self._comm.allreduce_(buf, stream=s)
-                    for r, o in enumerate(outs):
-                        o.copy_(buf[r * pad : r * pad + n].view_as(o))
+                    # gather straight into the caller's tensors when they are one contiguous block, else through a flat buffer
+                    n = inp.numel() * inp.element_size()
+                    base = outs[0].data_ptr()
+                    if all(o.data_ptr() == base + r * n and o.numel() * o.element_size() == n for r, o in enumerate(outs)):
+                        from torchft_b200.parallel.symm_mem import tensor_from_ptr
 
-            return self._launch(run, output_tensors)
+                        flat = tensor_from_ptr(base, n * self._world, self._device)
+                        self._comm.allgather_(flat, inp, stream=s)
+                    else:
+                        flat = torch.empty(self._world * inp.numel(), dtype=inp.dtype, device=inp.device)
+                        self._comm.allgather_(flat, inp, stream=s)
+                        for r, o in enumerate(outs):
+                            o.copy_(flat[r * inp.numel():(r + 1) * inp.numel()].view_as(o))
+
+            return self._launch(run, [t for o in output_tensors for t in o])
         return self._get_sidecar().allgather(output_tensors, input_tensor, opts)
 
     def allgather_into_tensor_coalesced(self, output_tensors: List[torch.Tensor], input_tensors: List[torch.Tensor], opts: Any) -> Work:
-        if all(self._native_ok(t) for t in input_tensors) and all(self._native_ok(t) for t in output_tensors):
+        if all(self._raw_ok(t) for t in input_tensors) and all(self._raw_ok(t) for t in output_tensors):
             def run(s: torch.cuda.Stream) -> None:
                 for out, inp in zip(output_tensors, input_tensors):
-                    n = inp.numel()
-                    assert out.numel() == n * self._world
-                    flat = out.view(-1)
-                    flat.zero_()
-                    flat[self._rank * n : (self._rank + 1) * n].copy_(inp.view(-1))
-                    self._comm.allreduce_(flat, stream=s)
+                    assert out.numel() == inp.numel() * self._world
+                    self._comm.allgather_(out, inp, stream=s)
 
             return self._launch(run, output_tensors)
         return self._get_sidecar().allgather_into_tensor_coalesced(output_tensors, input_tensors, opts)
 
-    def reduce_scatter(self, output_tensors: List[torch.Tensor], input_tensors: List[List[torch.Tensor]], opts: Any) -> Work:
+    def _reduce_kind(self, opts: Any, tensors: List[torch.Tensor]) -> Optional[tuple]:
         op = _reduce_op(opts)
-        flat_ok = all(self._native_ok(t) for ins in input_tensors for t in ins)
-        if flat_ok and (op in _OPS or op == ReduceOp.AVG):
-            scale = 1.0 / self._world if op == ReduceOp.AVG else 1.0
-            code = _OPS.get(op, _native.OP_SUM)
+        if (op in _OPS or op == ReduceOp.AVG) and all(self._raw_ok(t) and t.dtype in _NATIVE_DTYPES for t in tensors):
+            return _OPS.get(op, _native.OP_SUM), (1.0 / self._world if op == ReduceOp.AVG else 1.0)
+        return None
+
+    def reduce_scatter(self, output_tensors: List[torch.Tensor], input_tensors: List[List[torch.Tensor]], opts: Any) -> Work:
+        flat_in = [t for ins in input_tensors for t in ins]
+        kind = self._reduce_kind(opts, flat_in + list(output_tensors))
+        if kind is not None:
+            code, scale = kind
 
             def run(s: torch.cuda.Stream) -> None:
                 for out, ins in zip(output_tensors, input_tensors):
-                    buf = torch.cat([t.reshape(-1) for t in ins])
-                    self._comm.allreduce_(buf, op=code, scale=scale, stream=s)
-                    n = out.numel()
-                    out.copy_(buf[self._rank * n : (self._rank + 1) * n].view_as(out))
+                    n = out.numel() * out.element_size()
+                    base = ins[0].data_ptr()
+                    if all(t.data_ptr() == base + r * n for r, t in enumerate(ins)):
+                        from torchft_b200.parallel.symm_mem import tensor_from_ptr
+
+                        buf = tensor_from_ptr(base, n * self._world, self._device).view(out.dtype)
+                    else:
+                        buf = torch.cat([t.reshape(-1) for t in ins])
+                    self._comm.reduce_scatter_(out, buf, op=code, scale=scale, stream=s)
 
             return self._launch(run, output_tensors)
         return self._get_sidecar().reduce_scatter(output_tensors, input_tensors, opts)
 
     def reduce_scatter_tensor_coalesced(self, output_tensors: List[torch.Tensor], input_tensors: List[torch.Tensor], opts: Any) -> Work:
-        op = _reduce_op(opts)
-        if all(self._native_ok(t) for t in input_tensors) and (op in _OPS or op == ReduceOp.AVG):
-            scale = 1.0 / self._world if op == ReduceOp.AVG else 1.0
-            code = _OPS.get(op, _native.OP_SUM)
+        kind = self._reduce_kind(opts, list(input_tensors) + list(output_tensors))
+        if kind is not None:
+            code, scale = kind
 
             def run(s: torch.cuda.Stream) -> None:
                 for out, inp in zip(output_tensors, input_tensors):
-                    buf = inp.reshape(-1).clone()
-                    self._comm.allreduce_(buf, op=code, scale=scale, stream=s)
-                    n = out.numel()
-                    out.copy_(buf[self._rank * n : (self._rank + 1) * n].view_as(out))
+                    self._comm.reduce_scatter_(out, inp, op=code, scale=scale, stream=s)
 
             return self._launch(run, output_tensors)
         return self._get_sidecar().reduce_scatter_tensor_coalesced(output_tensors, input_tensors, opts)
 
     def alltoall_base(self, output_buffer: torch.Tensor, input_buffer: torch.Tensor, output_split_sizes: List[int],
                       input_split_sizes: List[int], opts: Any) -> Work:
+        w = self._world
+        equal = ((not output_split_sizes or len(set(output_split_sizes)) == 1) and (not input_split_sizes or len(set(input_split_sizes)) == 1)
+                 and input_buffer.numel() % max(w, 1) == 0
+                 and input_buffer.numel() * input_buffer.element_size() == output_buffer.numel() * output_buffer.element_size())
+        if equal and self._raw_ok(output_buffer) and self._raw_ok(input_buffer):
+            return self._launch(lambda s: self._comm.alltoall_(output_buffer, input_buffer, stream=s), output_buffer)
+        # unequal splits: a rank only knows its own row and column of the split matrix, so the ranks cannot agree on
+        # the number of staging rounds without an extra exchange -- left to the library path
         return self._get_sidecar().alltoall_base(output_buffer, input_buffer, output_split_sizes, input_split_sizes, opts)
 
+    def _p2p_launch(self, stream: torch.cuda.Stream, fn: Any, tensors: List[torch.Tensor]) -> Work:
+        latched = self._comm.errored() or self._aborted
+        if latched is not None:
+            raise latched
+        stream.wait_stream(torch.cuda.current_stream(self._device))
+        with torch.cuda.stream(stream):
+            fn(stream)
+            ev = stream.record_event()
+        for t in tensors:
+            t.record_stream(stream)
+        return StreamWork(ev, tensors)
+
     def send(self, tensors: List[torch.Tensor], dst_rank: int, tag: int) -> Work:
+        """Per-pair FIFO over the receiver's mailbox (tags are not matched, like NCCL). Sends and receives run on
+        two dedicated streams, so a rank that posts ``send`` then ``recv`` cannot dead-lock against a peer doing the same."""
+        if all(self._raw_ok(t) for t in tensors):
+            def run(s: torch.cuda.Stream) -> None:
+                for t in tensors:
+                    self._comm.send_(t, dst_rank, stream=s)
+
+            return self._p2p_launch(self._send_stream, run, tensors)
         return self._get_sidecar().send(tensors, dst_rank, tag)
 
     def recv(self, tensors: List[torch.Tensor], src_rank: int, tag: int) -> Work:
+        if all(self._raw_ok(t) for t in tensors):
+            def run(s: torch.cuda.Stream) -> None:
+                for t in tensors:
+                    self._comm.recv_(t, src_rank, stream=s)
+
+            return self._p2p_launch(self._recv_stream, run, tensors)
         return self._get_sidecar().recv(tensors, src_rank, tag)
 
     def __repr__(self) -> str:

@@ -102,6 +102,12 @@ class SymmetricComm:
         if staging_bytes is None:
             staging_bytes = int(os.environ.get("TORCHFT_B200_STAGING_MB", "256")) << 20
         self._staging_bytes = (staging_bytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        # the tail of the staging buffer holds one send/recv mailbox per source rank; collectives use the head
+        self._mailbox_bytes = min(4 << 20, (self._staging_bytes // 4 // 8) & ~15)
+        self._mailbox_off = self._staging_bytes - 8 * self._mailbox_bytes
+        self._staging_usable = self._mailbox_off
+        self._send_seq: Dict[int, int] = {}
+        self._recv_seq: Dict[int, int] = {}
         self._pad_bytes = (self._K.SIGNAL_PAD_BYTES + 65535) // 65536 * 65536
         self._max_blocks = int(os.environ.get("TORCHFT_B200_AR_BLOCKS", "64"))
         self._threads = int(os.environ.get("TORCHFT_B200_AR_THREADS", "512"))
@@ -256,12 +262,14 @@ class SymmetricComm:
                     self._setup_multicast(store, descs, [n for n in names if n != "core"], rank, world)
                 self._configured = True
 
-    def _install(self, ptrs: Dict[str, List[int]], rank: int, world: int, epoch: int, floor: int) -> None:
+    def _install(self, ptrs: Dict[str, List[int]], rank: int, world: int, epoch: int, floor: int,
+                 pads: Optional[List[int]] = None) -> None:
         """Build the per-segment peer tables from mapped base pointers and restart the flag sequence."""
         K = self._K
         self._ptrs = ptrs
         core_ptrs = ptrs["core"]
-        pads = core_ptrs  # signal pad sits at offset 0 of the core segment
+        if pads is None:
+            pads = core_ptrs  # signal pad sits at offset 0 of the core segment
         self._tables = {}
         base = K.PeerTable([p + self._pad_bytes for p in core_ptrs], pads, rank, world)
         base.set_timeout_ms(self._timeout.total_seconds() * 1e3)
@@ -271,6 +279,7 @@ class SymmetricComm:
                 self._tables[n] = base.with_data(ptrs[n])
         self._flag = max(floor, int(epoch) << 32) + 16
         self._rank, self._world, self._epoch = rank, world, int(epoch)
+        self._send_seq, self._recv_seq = {}, {}
         self._nvls_min = self._nvls_min_env if self._nvls_min_env is not None else self._default_nvls_min(world)
 
     @staticmethod
@@ -296,11 +305,16 @@ class SymmetricComm:
         names = list(comms[0]._segments)
         ptrs = {n: [c._segments[n].ptr for c in comms] for n in names}
         for r, c in enumerate(comms):
-            c._install({n: list(v) for n, v in ptrs.items()}, r, world, epoch=1, floor=0)
-            c._configured = True
+            pads = None
             if presignal:
+                # own pad: every slot reads "arrived" (>= any flag) and "verdict ok" (odd) forever; the flags this rank
+                # publishes go to a private sink instead of the peers' pads, so nothing ever un-signals a slot
                 pad = c._segments["core"].tensor[: c._K.SIGNAL_PAD_BYTES].view(torch.int64)
-                pad.fill_((1 << 62) | 1)  # ">= any flag" and "verdict ok" at once
+                pad.fill_((1 << 62) | 1)
+                c._sink = torch.zeros(c._K.SIGNAL_PAD_BYTES, dtype=torch.uint8, device=c.device)
+                pads = [c._segments["core"].ptr if t == r else c._sink.data_ptr() for t in range(world)]
+            c._install({n: list(v) for n, v in ptrs.items()}, r, world, epoch=1, floor=0, pads=pads)
+            c._configured = True
         torch.cuda.synchronize(comms[0].device)
         return comms
 
@@ -426,7 +440,7 @@ class SymmetricComm:
                 return
             if t.data_ptr() % 16:
                 raise ValueError("allreduce_ needs a 16-byte aligned tensor")
-            max_elems = self._staging_bytes // es
+            max_elems = self._staging_usable // es
             flat = t.view(-1)
             for lo in range(0, flat.numel(), max_elems):
                 n = min(max_elems, flat.numel() - lo)
@@ -468,7 +482,7 @@ class SymmetricComm:
                 return
             es = a.element_size()
             # elements per launch such that the Q8G buffer fits in staging
-            per = (self._staging_bytes * 512 // 516) // (512 * self._world) * (512 * self._world) - 512 * self._world
+            per = (self._staging_usable * 512 // 516) // (512 * self._world) * (512 * self._world) - 512 * self._world
             fo, fa = out.view(-1), a.view(-1)
             fb = b.view(-1) if b is not None else None
             for lo in range(0, fa.numel(), per):
@@ -478,6 +492,142 @@ class SymmetricComm:
                                (fb.data_ptr() + lo * es) if fb is not None else 0, fo.data_ptr() + lo * es, n, dt,
                                scale, self._next_flag(), _CH_Q8, contribute, blocks, self._barrier_mode, sp)
                 self.launches += 1
+
+    # ------------------------------------------------------------------ the rest of the collective surface
+    def _xblocks(self, nbytes: int) -> int:
+        return max(1, min(self._max_blocks, self._K.MAX_BLOCKS, nbytes // (64 << 10)))
+
+    def _exchange(self, inp: int, out: int, send: List[Tuple[int, int]], recv: List[Tuple[int, int]], stream: Any) -> None:
+        """One push-exchange launch per staging round. ``send[p] = (offset, bytes)`` into ``inp`` owed to rank p,
+        ``recv[p] = (offset, bytes)`` into ``out`` expected from rank p. Every rank must derive the same number of
+        rounds, i.e. callers only pass messages whose length is known quorum-wide."""
+        W = self._world
+        stride = (self._staging_usable // W) & ~15
+        longest = max([n for _, n in send] + [n for _, n in recv] + [0])
+        if longest == 0:
+            return
+        sp = _native.stream_ptr(stream)
+        for lo in range(0, longest, stride):
+            s_off = [o + min(lo, n) for o, n in send]
+            s_len = [max(0, min(stride, n - lo)) for _, n in send]
+            r_off = [o + min(lo, n) for o, n in recv]
+            r_len = [max(0, min(stride, n - lo)) for _, n in recv]
+            self._K.push_exchange(self._tables["core"], self._status, inp, out, s_off, s_len, r_len, r_off, stride,
+                                  self._next_flag(), _CH_ALLREDUCE, self._xblocks(max(s_len + r_len)), self._barrier_mode, sp)
+            self.launches += 1
+
+    @staticmethod
+    def _check_raw(*ts: torch.Tensor) -> None:
+        for t in ts:
+            if not t.is_cuda or not t.is_contiguous():
+                raise ValueError("native collectives need contiguous CUDA tensors")
+
+    def allgather_(self, out: torch.Tensor, inp: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """``out[r*n:(r+1)*n] = inp of rank r`` (any dtype; moves (W-1)*n bytes out of every rank)."""
+        self._check_raw(out, inp)
+        n = inp.numel() * inp.element_size()
+        assert out.numel() * out.element_size() == n * max(self._world, 1)
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            if self._world == 1:
+                if out.data_ptr() != inp.data_ptr():
+                    out.view(-1).view(torch.uint8)[:n].copy_(inp.view(-1).view(torch.uint8))
+                return
+            W = self._world
+            self._exchange(inp.data_ptr(), out.data_ptr(), [(0, n)] * W, [(p * n, n) for p in range(W)], stream)
+
+    def broadcast_(self, t: torch.Tensor, root: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Root's ``t`` lands in everybody's ``t`` (root stores into the peers' staging slots; n bytes per peer link)."""
+        self._check_raw(t)
+        n = t.numel() * t.element_size()
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            if self._world == 1:
+                return
+            W, me = self._world, self._rank
+            send = [(0, n if (me == root and p != me) else 0) for p in range(W)]
+            recv = [(0, n if (p == root and me != root) else 0) for p in range(W)]
+            self._exchange(t.data_ptr(), t.data_ptr(), send, recv, stream)
+
+    def alltoall_(self, out: torch.Tensor, inp: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Equal-split all-to-all: chunk p of ``inp`` goes to rank p, where it becomes chunk ``rank`` of ``out``."""
+        self._check_raw(out, inp)
+        nb = inp.numel() * inp.element_size()
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            W = max(self._world, 1)
+            if nb % W or out.numel() * out.element_size() != nb:
+                raise ValueError("alltoall_: buffers must have equal size divisible by the world size")
+            if W == 1:
+                if out.data_ptr() != inp.data_ptr():
+                    out.view(-1).view(torch.uint8).copy_(inp.view(-1).view(torch.uint8))
+                return
+            c = nb // W
+            self._exchange(inp.data_ptr(), out.data_ptr(), [(p * c, c) for p in range(W)], [(p * c, c) for p in range(W)], stream)
+
+    def reduce_scatter_(self, out: torch.Tensor, inp: torch.Tensor, op: int = _native.OP_SUM, scale: float = 1.0,
+                        stream: Optional[torch.cuda.Stream] = None) -> None:
+        """``out = scale * reduce over ranks of inp[rank*n:(rank+1)*n]`` (fp32 accumulate, fixed rank order)."""
+        self._check_raw(out, inp)
+        dt = _native.dtype_code(inp)
+        n, es = out.numel(), inp.element_size()
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            W = max(self._world, 1)
+            assert inp.numel() == n * W and out.dtype == inp.dtype
+            if W == 1:
+                torch.mul(inp.view(-1), scale, out=out.view(-1)) if scale != 1.0 else out.view(-1).copy_(inp.view(-1))
+                return
+            sp = _native.stream_ptr(stream)
+            hit = self._segment_of(inp)
+            if hit is not None and hit[0].name != "core" and hit[1] % 16 == 0:
+                seg, off = hit  # zero-copy: peers read the input where it lives
+                self._K.reduce_scatter(self._tables[seg.name], self._status, off, 0, out.data_ptr(), n, dt, op, scale,
+                                       self._next_flag(), _CH_ALLREDUCE, self._xblocks(n * es), self._barrier_mode, sp)
+                self.launches += 1
+                return
+            per = (self._staging_usable // (W * es)) // 8 * 8  # elements of every slot per round (16 B aligned slots)
+            if n <= per:
+                self._K.reduce_scatter(self._tables["core"], self._status, 0, inp.data_ptr(), out.data_ptr(), n, dt, op, scale,
+                                       self._next_flag(), _CH_ALLREDUCE, self._xblocks(n * es), self._barrier_mode, sp)
+                self.launches += 1
+                return
+            rows, flat_out = inp.view(W, n), out.view(-1)
+            for lo in range(0, n, per):  # larger than staging: one strided gather per round
+                hi = min(n, lo + per)
+                piece = rows[:, lo:hi].contiguous()
+                self._K.reduce_scatter(self._tables["core"], self._status, 0, piece.data_ptr(), flat_out[lo:hi].data_ptr(), hi - lo, dt,
+                                       op, scale, self._next_flag(), _CH_ALLREDUCE, self._xblocks((hi - lo) * es), self._barrier_mode, sp)
+                piece.record_stream(stream if stream is not None else torch.cuda.current_stream())
+                self.launches += 1
+
+    def _p2p(self, is_send: bool, t: torch.Tensor, peer: int, stream: Optional[torch.cuda.Stream]) -> None:
+        self._check_raw(t)
+        nbytes = t.numel() * t.element_size()
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            if nbytes == 0:
+                return
+            book = self._send_seq if is_send else self._recv_seq
+            seq = book.get(peer, 0) + 1
+            pieces = (nbytes + self._mailbox_bytes - 1) // self._mailbox_bytes
+            book[peer] = seq + pieces - 1
+            self._K.p2p(self._tables["core"], self._status, is_send, t.data_ptr(), nbytes, peer, self._mailbox_off,
+                        self._mailbox_bytes, (self._epoch << 32) + seq, _CH_USER, _native.stream_ptr(stream))
+            self.launches += 1
+
+    def send_(self, t: torch.Tensor, dst: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Stream ``t`` into rank ``dst``'s mailbox (pieces of <= 4 MiB, flow-controlled by its acks)."""
+        self._p2p(True, t, dst, stream)
+
+    def recv_(self, t: torch.Tensor, src: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Receive the next message of rank ``src`` (FIFO per ordered pair; tags are not matched) into ``t``."""
+        self._p2p(False, t, src, stream)
 
     # ------------------------------------------------------------------ FT-ZeRO-1 (csrc/kernels/zero1.cu)
     def peer_pointers(self, name: str) -> List[int]:
