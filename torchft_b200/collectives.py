@@ -206,7 +206,17 @@ def reduce_scatter_quantized(output: torch.Tensor, inputs: List[torch.Tensor], o
             work_tensors.append(p)
             slices.append(p.numel() // world)
         es = work_tensors[0].element_size()
-        if any((s * es) % 16 for s in slices):
+        fused = getattr(process_group, "reduce_scatter_q8", None)
+        aligned = not any((s * es) % 16 for s in slices) and output.is_contiguous()
+        if fused is not None and aligned and world > 1 and all((sum(slices[:i]) * es) % 16 == 0 for i in range(len(slices))) \
+                and output.data_ptr() % 16 == 0:
+            # ProcessGroupB200: one kernel per tensor does quantise + exchange + reduce; no alltoall, no temporaries
+            scale = 1.0 / world if op == ReduceOp.AVG else 1.0
+            off = 0
+            for p, s in zip(work_tensors, slices):
+                fused(output[off: off + s], p.view(-1), s, scale=scale).wait()
+                off += s
+        elif any((s * es) % 16 for s in slices):
             # rows too narrow for aligned slices: reduce everything, keep our rows
             allreduce_quantized(work_tensors, op, process_group, stream).wait()
             off = 0

@@ -244,6 +244,11 @@ class ProcessGroupB200(ProcessGroup):
         """Fused fp8 all-reduce of ``a - b`` (``b`` optional) into ``out``; one kernel, no NCCL."""
         return self._launch(lambda s: self._comm.q8_allreduce_(out, a, b, scale=scale, contribute=contribute, stream=s), out)
 
+    def reduce_scatter_q8(self, out: torch.Tensor, inp: torch.Tensor, slice_elems: int, scale: float = 1.0) -> Work:
+        """Fused fp8 reduce-scatter: ``out`` = this rank's ``slice_elems``-element slice of ``inp`` reduced over the
+        quorum (quantise + exchange + fp32 reduce in one kernel; no all-to-all call, no temporaries)."""
+        return self._launch(lambda s: self._comm.q8_reduce_scatter_(out, inp, slice_elems, scale=scale, stream=s), out)
+
     def allreduce(self, tensors: List[torch.Tensor], opts: Any) -> Work:
         op = _reduce_op(opts)
         if all(self._native_ok(t) for t in tensors) and (op in _OPS or op == ReduceOp.AVG):

@@ -109,7 +109,8 @@ class SymmetricComm:
         self._send_seq: Dict[int, int] = {}
         self._recv_seq: Dict[int, int] = {}
         self._pad_bytes = (self._K.SIGNAL_PAD_BYTES + 65535) // 65536 * 65536
-        self._max_blocks = int(os.environ.get("TORCHFT_B200_AR_BLOCKS", "64"))
+        self._max_blocks = max(1, min(int(os.environ.get("TORCHFT_B200_AR_BLOCKS", "64")), self._K.MAX_BLOCKS))
+        self._q8_max_blocks = 148  # phases A/C of the fp8 kernel are local HBM passes: use the whole chip
         self._threads = int(os.environ.get("TORCHFT_B200_AR_THREADS", "512"))
         self._oneshot_max = int(os.environ.get("TORCHFT_B200_ONESHOT_KB", "256")) << 10
         # "vmm": cuMemCreate-backed segments (survive exporter death, NVLS-capable); "ipc": cudaMalloc + cudaIpc
@@ -299,6 +300,8 @@ class SymmetricComm:
         comms = [SymmetricComm(device, staging_bytes=staging_bytes, timeout=timeout) for _ in range(world)]
         for c in comms:
             c._mode = "ipc"
+            # all ranks share ONE GPU: with real signalling every CTA of every rank must be resident at once
+            c._max_blocks = c._q8_max_blocks = max(2, 112 // world)
             c._ensure_core()
             for name, nbytes in segments.items():
                 c._alloc_segment(name, nbytes)
@@ -487,11 +490,34 @@ class SymmetricComm:
             fb = b.view(-1) if b is not None else None
             for lo in range(0, fa.numel(), per):
                 n = min(per, fa.numel() - lo)
-                blocks = max(4, min(148, (n // 512) // 32 + 1))  # phases A/C are local HBM passes: use the whole chip
+                blocks = max(4, min(self._q8_max_blocks, (n // 512) // 32 + 1))
                 K.q8_allreduce(self._tables["core"], self._status, 0, fa.data_ptr() + lo * es,
                                (fb.data_ptr() + lo * es) if fb is not None else 0, fo.data_ptr() + lo * es, n, dt,
                                scale, self._next_flag(), _CH_Q8, contribute, blocks, self._barrier_mode, sp)
                 self.launches += 1
+
+    def q8_reduce_scatter_(self, out: torch.Tensor, inp: torch.Tensor, slice_elems: int, scale: float = 1.0,
+                           contribute: bool = True, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """fp8 reduce-scatter in ONE launch: rank-slice s of ``inp`` is ``[s*slice_elems, (s+1)*slice_elems)``; ``out``
+        (``slice_elems`` elements) receives this rank's slice, fp32-reduced over the quorum and scaled. Quantise, exchange
+        and reduce happen inside the kernel (reference: collectives.py:159-294 = 2 kernels + alltoall + 2 allocations)."""
+        self._check_raw(out, inp)
+        dt = _native.dtype_code(inp)
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            W = self._world
+            if W < 2:
+                raise ValueError("q8_reduce_scatter_ needs a quorum of at least 2")
+            assert inp.numel() <= W * slice_elems and out.numel() >= min(slice_elems, max(0, inp.numel() - self._rank * slice_elems))
+            if self._K.q8_rs_buffer_bytes(slice_elems, W) > self._staging_usable:
+                raise ValueError("q8_reduce_scatter_: message larger than the staging segment")
+            groups = W * ((slice_elems + 511) // 512)
+            blocks = max(4, min(self._q8_max_blocks, groups // 32 + 1))
+            self._K.q8_reduce_scatter(self._tables["core"], self._status, 0, inp.data_ptr(), out.data_ptr(), inp.numel(), slice_elems,
+                                      dt, scale, self._next_flag(), _CH_Q8, contribute, blocks, self._barrier_mode,
+                                      _native.stream_ptr(stream))
+            self.launches += 1
 
     # ------------------------------------------------------------------ the rest of the collective surface
     def _xblocks(self, nbytes: int) -> int:
