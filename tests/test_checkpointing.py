@@ -242,3 +242,81 @@ def test_durable_checkpointer_roundtrip_rotation_and_torn_files(tmp_path):
     assert bad.maybe_save()
     with pytest.raises(RuntimeError, match="durable checkpoint write failed"):
         bad.wait()
+
+
+# ----------------------------------------------------------------------------- P2PTransport session lifetime
+def _p2p_source(timeout_s: float = 1.0):
+    from datetime import timedelta
+
+    from torchft_b200.checkpointing.p2p_transport import P2PTransport
+
+    src = P2PTransport(timeout=timedelta(seconds=timeout_s))
+    src.send_checkpoint([1], 5, {"step": 5, "note": "tiny"}, timedelta(seconds=timeout_s))
+    return src
+
+
+def _open_session(src, step=5):
+    import http.client
+    from urllib.parse import urlparse
+
+    u = urlparse(src.metadata())
+    conn = http.client.HTTPConnection("127.0.0.1", u.port, timeout=5)
+    conn.request("GET", f"/manifest/{step}/deadbeef")
+    resp = conn.getresponse()
+    assert resp.status == 200
+    resp.read()
+    return conn
+
+
+def test_p2p_receiver_dying_mid_heal_releases_the_source():
+    import time
+
+    src = _p2p_source()
+    try:
+        conn = _open_session(src)
+        assert src._lock.w_locked()          # the session holds the read side
+        conn.sock.close()                     # SIGKILLed receiver: the kernel closes its sockets, no /done ever comes
+        t0 = time.monotonic()
+        src.disallow_checkpoint()             # must not raise and must not wait for the lock timeout
+        assert time.monotonic() - t0 < 0.9
+        # the transport stays usable: next send / disallow cycle works (the old code asserted on w_release here)
+        from datetime import timedelta
+
+        src.send_checkpoint([1], 6, {"step": 6}, timedelta(seconds=1))
+        src.disallow_checkpoint()
+    finally:
+        src.shutdown(wait=False)
+
+
+def test_p2p_wedged_receiver_is_evicted_after_the_lock_timeout():
+    import time
+
+    src = _p2p_source(timeout_s=0.5)
+    try:
+        conn = _open_session(src)             # fetched the manifest, then hangs forever without answering
+        t0 = time.monotonic()
+        src.disallow_checkpoint()             # waits the lock timeout once, evicts the session, then succeeds
+        took = time.monotonic() - t0
+        assert 0.4 < took < 3.0
+        assert not src._allowed and src._sessions == {}
+        conn.close()
+    finally:
+        src.shutdown(wait=False)
+
+
+def test_p2p_clean_session_roundtrip_of_small_objects():
+    from datetime import timedelta
+
+    from torchft_b200.checkpointing.p2p_transport import P2PTransport
+
+    src = _p2p_source()
+    dst = P2PTransport(timeout=timedelta(seconds=2))
+    try:
+        if torch.cuda.is_available():
+            got = dst.recv_checkpoint(0, src.metadata().replace(src.metadata().split("//")[1].rsplit(":", 1)[0], "127.0.0.1"), 5, timedelta(seconds=2))
+            assert got == {"step": 5, "note": "tiny"}
+        src.disallow_checkpoint()
+        assert not src._lock._readers
+    finally:
+        src.shutdown(wait=False)
+        dst.shutdown(wait=False)

@@ -68,9 +68,12 @@ def test_reduce_scatter_commit_update_match_reference(world, k):
                 acc += raw[r].float()
         reduced = (acc * (1.0 / contributors)).bfloat16()
 
-        for r, c in enumerate(comms):
+        # one-kernel-at-a-time emulation: the quiet rank zeroes its buffer inside its kernel, which on real hardware
+        # happens before anybody's push (barrier 1) -- so its kernel goes first here
+        order = ([quiet] if quiet is not None else []) + [r for r in range(world) if r != quiet]
+        for r in order:
             for lo, hi in UNITS:
-                c.zero1_reduce_scatter_("z1_grad", lo * 2, hi - lo, 1.0 / contributors, r != quiet, k, 4)
+                comms[r].zero1_reduce_scatter_("z1_grad", lo * 2, hi - lo, 1.0 / contributors, r != quiet, k, 4)
         torch.cuda.synchronize()
         for r in range(world):
             for lo, hi in L.held(r, world):

@@ -35,16 +35,8 @@ from torchft_b200.checkpointing.transport import CheckpointTransport
 logger = logging.getLogger(__name__)
 
 
-def _advertise_host() -> str:
-    """Hostname peers should dial; falls back to loopback when the hostname does not resolve
-    (common in containers) -- on-node transports only ever talk to the same host anyway."""
+from torchft_b200.checkpointing.transport import advertise_host as _advertise_host  # noqa: E402
 
-    h = socket.gethostname()
-    try:
-        socket.getaddrinfo(h, None)
-        return h
-    except OSError:
-        return "127.0.0.1"
 T = TypeVar("T")
 
 

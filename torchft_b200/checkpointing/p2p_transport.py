@@ -28,7 +28,6 @@ import logging
 import pickle
 import socket
 import threading
-import urllib.request
 from datetime import timedelta
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 from typing import Any, Callable, Dict, Generic, List, Optional, Sequence, Tuple, TypeVar
@@ -43,16 +42,8 @@ from torchft_b200.ops import _native
 logger = logging.getLogger(__name__)
 
 
-def _advertise_host() -> str:
-    """Hostname peers should dial; falls back to loopback when the hostname does not resolve
-    (common in containers) -- on-node transports only ever talk to the same host anyway."""
+from torchft_b200.checkpointing.transport import advertise_host as _advertise_host  # noqa: E402
 
-    h = socket.gethostname()
-    try:
-        socket.getaddrinfo(h, None)
-        return h
-    except OSError:
-        return "127.0.0.1"
 T = TypeVar("T")
 
 CHUNK_BYTES = 4 << 20
@@ -108,8 +99,9 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
         self._step = -1
         self._manifest: Optional[bytes] = None
         self._keepalive: Any = None
-        self._sessions: Dict[str, bool] = {}
+        self._sessions: Dict[str, Any] = {}  # session id -> its open connection (closing it releases its read lock)
         self._sess_lock = threading.Lock()
+        self._lease_s = max(1.0, timeout.total_seconds())
         self.last_recv_bytes = 0
         self.last_recv_ms = 0.0
         transport = self
@@ -127,29 +119,35 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
                 self.wfile.write(body)
 
             def do_GET(self) -> None:  # noqa: N802
-                # /manifest/{step}/{session}: take a read lock for the session
+                # /manifest/{step}/{session}: the read lock is held for as long as THIS connection lives. The receiver
+                # answers with one byte when its NVLink pull is done; a receiver that dies or is partitioned closes
+                # (or times out) the socket and the lock is released either way -- a leaked reader can never wedge the
+                # source's disallow_checkpoint (the reference's HTTP transport has the same property
+                # because it only holds the lock during the request, http_transport.py:38-298).
                 parts = self.path.strip("/").split("/")
                 try:
                     if len(parts) == 3 and parts[0] == "manifest":
                         step, sess = int(parts[1]), parts[2]
                         transport._lock.r_acquire()
-                        ok = False
                         try:
                             if step != transport._step or transport._manifest is None:
                                 return self._send(400, f"invalid checkpoint requested: serving {transport._step} but got {step}".encode())
                             with transport._sess_lock:
-                                transport._sessions[sess] = True
-                            ok = True
-                            return self._send(200, transport._manifest)
+                                transport._sessions[sess] = self.connection
+                            try:
+                                self._send(200, transport._manifest)
+                                self.connection.settimeout(transport._lease_s)
+                                try:
+                                    self.connection.recv(1)  # b"D" = done, b"" = peer went away, timeout = lease over
+                                except OSError:
+                                    pass
+                            finally:
+                                with transport._sess_lock:
+                                    transport._sessions.pop(sess, None)
+                                self.close_connection = True
                         finally:
-                            if not ok:
-                                transport._lock.r_release()
-                    if len(parts) == 2 and parts[0] == "done":
-                        with transport._sess_lock:
-                            held = transport._sessions.pop(parts[1], False)
-                        if held:
                             transport._lock.r_release()
-                        return self._send(200, b"ok")
+                        return
                     self._send(404, b"unknown path")
                 except TimeoutError as e:
                     self._send(503, f"checkpoint not available: {e}".encode())
@@ -175,10 +173,15 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
         if torch.cuda.is_available():
             torch.cuda.current_stream().synchronize()
         for leaf in leaves:
-            if isinstance(leaf, torch.Tensor) and leaf.is_cuda:
+            host = isinstance(leaf, torch.Tensor) and not leaf.is_cuda and leaf.numel() * leaf.element_size() >= 4096
+            if (isinstance(leaf, torch.Tensor) and leaf.is_cuda) or host:
                 t = leaf.detach()
                 if isinstance(t, torch.distributed.tensor.DTensor):  # type: ignore[attr-defined]
                     t = t.to_local()
+                if host:
+                    # CPU tensors (e.g. DiLoCo's pinned backup weights) ride the same NVLink pull: stage them on the GPU
+                    # once instead of embedding them in the manifest (that doubled them as hex in memory)
+                    t = t.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
                 # bytes actually backing this view
                 if not t.is_contiguous():
                     t = t.contiguous()
@@ -190,36 +193,75 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
                     handles[base] = K.ipc_get_handle(base).hex()
                 items.append({"k": "cuda", "base": base, "off": ptr - base, "nbytes": nbytes,
                               "dtype": str(t.dtype).replace("torch.", ""), "shape": list(t.shape),
-                              "device": t.device.index})
+                              "device": t.device.index, "host": host})
             else:
-                items.append({"k": "obj", "data": pickle.dumps(leaf).hex()})
+                items.append({"k": "obj", "data": pickle.dumps(leaf)})
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()  # staged host tensors have landed
         self._keepalive = keep
-        self._manifest = pickle.dumps({"spec": spec, "items": items, "handles": handles, "pid": _pid()})
+        self._manifest = pickle.dumps({"spec": spec, "items": items, "handles": handles, "pid": _pid(),
+                                       "host": socket.gethostname()})
         self._step = step
         if not self._allowed:
             self._allowed = True
             self._lock.w_release()
 
+    def _drop_sessions(self) -> None:
+        """Cut the connections of sessions that are still open: their handlers wake up and release the read lock."""
+        with self._sess_lock:
+            conns = list(self._sessions.items())
+        for sess, conn in conns:
+            logger.warning("p2p_transport: dropping stale heal session %s", sess)
+            try:
+                conn.shutdown(socket.SHUT_RDWR)
+            except OSError:
+                pass
+
     def disallow_checkpoint(self) -> None:
-        if self._allowed:
-            self._allowed = False
+        if not self._allowed:
+            return
+        try:
             self._lock.w_acquire()  # waits for sessions still pulling
-            self._manifest = None
-            self._keepalive = None
+        except TimeoutError:
+            # a reader outlived the lock timeout (receiver wedged or partitioned): evict it rather than failing the
+            # training step, and only give up if even that does not free the lock
+            self._drop_sessions()
+            self._lock.w_acquire()
+        self._allowed = False  # flipped only once the write lock is really held, so the two can never disagree
+        self._manifest = None
+        self._keepalive = None
 
     # ---------------------------------------------------------------- receiver
     def recv_checkpoint(self, src_rank: int, metadata: str, step: int, timeout: timedelta) -> T:
         K = _native.load()
         import uuid
 
+        import http.client
+        from urllib.parse import urlparse
+
         sess = uuid.uuid4().hex
+        u = urlparse(metadata)
+        conn = http.client.HTTPConnection(u.hostname, u.port, timeout=timeout.total_seconds())
         try:
-            with urllib.request.urlopen(f"{metadata}/manifest/{step}/{sess}", timeout=timeout.total_seconds()) as r:
-                man = pickle.loads(r.read())
-        except urllib.error.HTTPError as e:  # type: ignore[attr-defined]
-            raise RuntimeError(f"checkpoint fetch from rank {src_rank} failed: {e.code} {e.read().decode(errors='replace')}") from e
+            conn.request("GET", f"/manifest/{step}/{sess}")
+            resp = conn.getresponse()
+            body = resp.read()
         except (socket.timeout, TimeoutError) as e:
+            conn.close()
             raise TimeoutError(f"checkpoint manifest from rank {src_rank} timed out: {e}") from e
+        except OSError as e:
+            conn.close()
+            raise RuntimeError(f"checkpoint fetch from rank {src_rank} failed: {e}") from e
+        if resp.status != 200:
+            conn.close()
+            if resp.status == 503:
+                raise TimeoutError(f"checkpoint fetch from rank {src_rank} failed: {resp.status} {body.decode(errors='replace')}")
+            raise RuntimeError(f"checkpoint fetch from rank {src_rank} failed: {resp.status} {body.decode(errors='replace')}")
+        man = pickle.loads(body)
+        if man.get("host", socket.gethostname()) != socket.gethostname():
+            conn.close()
+            raise RuntimeError(f"P2PTransport only works inside one host (NVLink/CUDA-IPC): source is on {man['host']!r}, "
+                               f"we are on {socket.gethostname()!r}; use HTTPTransport or PGTransport across hosts")
         opened: Dict[int, int] = {}
         try:
             same_process = man["pid"] == _pid()
@@ -238,15 +280,20 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
                 for kp, idx in pytree.tree_flatten_with_path(index_tree)[0]:
                     dst_leaves[idx] = targets.get(pytree.keystr(kp))
             out: List[Any] = []
+            host_moves: List[Tuple[int, torch.Tensor, Optional[torch.Tensor]]] = []
             entries: List[Tuple[int, int, int]] = []
             total = 0
             dev = torch.device("cuda", torch.cuda.current_device())
             for i, it in enumerate(man["items"]):
                 if it["k"] == "obj":
-                    out.append(pickle.loads(bytes.fromhex(it["data"])))
+                    data = it["data"]
+                    out.append(pickle.loads(bytes.fromhex(data) if isinstance(data, str) else data))
                     continue
                 dtype = getattr(torch, it["dtype"])
                 dst = None
+                host_target = None
+                if it.get("host") and dst_leaves is not None and isinstance(dst_leaves[i], torch.Tensor) and not dst_leaves[i].is_cuda:
+                    host_target = dst_leaves[i]
                 if dst_leaves is not None and isinstance(dst_leaves[i], torch.Tensor):
                     cand = dst_leaves[i]
                     cand_local = cand.to_local() if hasattr(cand, "to_local") else cand
@@ -259,6 +306,8 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
                 if it["nbytes"]:
                     entries.append((opened[it["base"]] + it["off"], dptr, it["nbytes"]))
                     total += it["nbytes"]
+                if it.get("host"):
+                    host_moves.append((len(out), dst, host_target))
                 out.append(dst)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -266,6 +315,12 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
             e.record()
             e.synchronize()
             self.last_recv_bytes, self.last_recv_ms = total, s.elapsed_time(e)
+            for idx, staged, target in host_moves:  # leaves that were CPU tensors on the source go back to the host
+                if target is not None and target.shape == staged.shape and target.dtype == staged.dtype:
+                    target.copy_(staged)
+                    out[idx] = target
+                else:
+                    out[idx] = staged.cpu()
             return pytree.tree_unflatten(out, man["spec"])
         finally:
             for base, p in opened.items():
@@ -275,9 +330,10 @@ class P2PTransport(CheckpointTransport[T], Generic[T]):
                     except RuntimeError:
                         pass
             try:
-                urllib.request.urlopen(f"{metadata}/done/{sess}", timeout=timeout.total_seconds()).read()
-            except Exception:
-                logger.warning("p2p_transport: failed to release session on source")
+                conn.sock.sendall(b"D")  # done: the source releases this session's read lock
+            except Exception:  # noqa: BLE001 - closing the socket releases it as well
+                pass
+            conn.close()
 
     def shutdown(self, wait: bool = True) -> None:
         self._server.shutdown()

@@ -39,3 +39,36 @@ class CheckpointTransport(Generic[T], ABC):
 
     def shutdown(self, wait: bool = True) -> None:
         """Release sockets/threads."""
+
+
+def advertise_host() -> str:
+    """Address peers should dial to reach a server of this process.
+
+    ``TORCHFT_ADVERTISE_HOST`` wins; else the hostname when it resolves (the reference uses ``socket.gethostname()``,
+    http_transport.py); else the address of the interface that routes off-host, so cross-node peers still get
+    something dialable; loopback only as a logged last resort (single-box containers whose hostname does not resolve).
+    """
+    import logging
+    import os
+    import socket
+
+    env = os.environ.get("TORCHFT_ADVERTISE_HOST")
+    if env:
+        return env
+    h = socket.gethostname()
+    try:
+        socket.getaddrinfo(h, None)
+        return h
+    except OSError:
+        pass
+    try:
+        with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s:
+            s.connect(("10.255.255.255", 1))  # no packet is sent; the kernel just picks the outbound interface
+            ip = s.getsockname()[0]
+        if not ip.startswith("127."):
+            return ip
+    except OSError:
+        pass
+    logging.getLogger(__name__).warning("hostname %r does not resolve and no routable interface was found: advertising "
+                                        "127.0.0.1 (peers on other hosts cannot reach this transport)", h)
+    return "127.0.0.1"
