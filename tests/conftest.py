@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# The in-process multi-rank GPU tests launch several kernels that wait for EACH OTHER on different streams; streams that
+# share a hardware work queue would order them falsely (a kernel queued behind one that waits for it). More queues
+# (must be set before CUDA initialises) make that impossible for the handful of streams the tests use.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

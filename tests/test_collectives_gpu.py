@@ -140,18 +140,12 @@ def test_send_recv_multi_piece_fifo():
     ra, rb = torch.empty_like(a), torch.empty_like(b)
     back = torch.empty_like(b)
 
-    def go(r, c, s):
-        if r == 0:
-            c.send_(a, 2, s)
-            c.send_(b, 2, s)
-        elif r == 2:
-            c.recv_(ra, 0, s)
-            c.recv_(rb, 0, s)
-            c.send_(rb, 1, s)
-        else:
-            c.recv_(back, 2, s)
-
-    _run(comms, go)
+    # one kernel per stream and phase: inside ONE process a second kernel queued behind a waiting one could be ordered
+    # in front of the kernel it waits for (real ranks are separate processes with their own queues)
+    _run(comms, lambda r, c, s: c.send_(a, 2, s) if r == 0 else c.recv_(ra, 0, s), ranks=(0, 2))
+    _ok(comms)
+    _run(comms, lambda r, c, s: c.send_(b, 2, s) if r == 0 else c.recv_(rb, 0, s), ranks=(0, 2))
+    _run(comms, lambda r, c, s: c.send_(rb, 1, s) if r == 2 else c.recv_(back, 2, s), ranks=(1, 2))
     _ok(comms)
     assert torch.equal(ra, a) and torch.equal(rb, b) and torch.equal(back, b)
 

@@ -18,8 +18,9 @@ from torchft_b200.process_group import (
     ProcessGroupDummy,
     ProcessGroupGloo,
     ProcessGroupNCCL,
+    ProcessGroupXCCL,
 )
-from torchft_b200.baby import ProcessGroupBabyGloo, ProcessGroupBabyNCCL
+from torchft_b200.baby import ProcessGroupBabyGloo, ProcessGroupBabyNCCL, ProcessGroupBabyXCCL
 
 for _name in ("torchft_quorums", "torchft_commits", "torchft_errors"):
     _setup_logger(_name)
@@ -44,7 +45,9 @@ __all__ = [
     "ManagedProcessGroup",
     "ProcessGroupB200",
     "ProcessGroupNCCL",
+    "ProcessGroupXCCL",
     "ProcessGroupBabyNCCL",
+    "ProcessGroupBabyXCCL",
     "ProcessGroupBabyGloo",
     "ProcessGroupGloo",
     "ProcessGroupDummy",

@@ -39,7 +39,7 @@ from torch.distributed.distributed_c10d import (
 from torch.futures import Future
 
 from torchft_b200.multiprocessing import MonitoredPipe, failure_of
-from torchft_b200.process_group import _FORWARDED, ProcessGroup, ProcessGroupGloo, ProcessGroupNCCL
+from torchft_b200.process_group import _FORWARDED, ProcessGroup, ProcessGroupGloo, ProcessGroupNCCL, ProcessGroupXCCL
 
 logger = logging.getLogger(__name__)
 
@@ -380,6 +380,12 @@ class ProcessGroupBabyGloo(ProcessGroupBaby):
 
     def reduce_scatter_tensor_coalesced(self, *a: Any) -> Work:
         raise RuntimeError("ProcessGroupBabyGloo does not support reduce_scatter_tensor_coalesced.")
+
+
+class ProcessGroupBabyXCCL(ProcessGroupBaby):
+    """XCCL in a subprocess (reference: process_group.py:2081+). API parity for Intel XPUs; see ``ProcessGroupXCCL``."""
+
+    PG_CLASS = ProcessGroupXCCL
 
 
 class ProcessGroupBabyNCCL(ProcessGroupBaby):

@@ -90,6 +90,8 @@ void xent_launch(void* logits, const void* target, float* loss, size_t rows, int
 void adamw_launch(void* p, float* master, float* m, float* v, const void* g, size_t n, float lr,
                   float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
                   const int* gate, int max_blocks, cudaStream_t s);
+void diloco_outer_launch(void* param, void* original, const void* grad, float* mom, size_t n, int dtype, float lr,
+                         float mu, int nesterov, float alpha, const int* gate, cudaStream_t s);
 void sumsq_launch(const void* g, size_t n, float* out, cudaStream_t s);
 void heal_copy_launch(const void* table_dev, int nentries, size_t total_chunks, size_t chunk_bytes,
                       int blocks, cudaStream_t s);

@@ -375,6 +375,12 @@ PYBIND11_MODULE(_K, m) {
   }, py::arg("p"), py::arg("master"), py::arg("m"), py::arg("v"), py::arg("g"), py::arg("n"), py::arg("lr"),
      py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("bc1"), py::arg("bc2"),
      py::arg("gscale"), py::arg("gate"), py::arg("stream"), py::arg("max_blocks") = 0);
+  m.def("diloco_outer", [](uintptr_t param, uintptr_t original, uintptr_t grad, uintptr_t mom, size_t n, int dtype, float lr,
+                            float mu, bool nesterov, float alpha, uintptr_t gate, uintptr_t s) {
+    diloco_outer_launch(P<void>(param), P<void>(original), P<void>(grad), P<float>(mom), n, dtype, lr, mu, nesterov ? 1 : 0,
+                        alpha, P<const int>(gate), S(s));
+  }, py::arg("param"), py::arg("original"), py::arg("grad"), py::arg("mom"), py::arg("n"), py::arg("dtype"), py::arg("lr"),
+     py::arg("mu"), py::arg("nesterov"), py::arg("alpha"), py::arg("gate"), py::arg("stream"));
   m.def("sumsq", [](uintptr_t g, size_t n, uintptr_t out, uintptr_t s) {
     sumsq_launch(P<void>(g), n, P<float>(out), S(s));
   });

@@ -349,6 +349,57 @@ __global__ void __launch_bounds__(512, 2) adamw_kernel(AdamArgs a) {
   }
 }
 
+// DiLoCo outer step, fused: averaged pseudo-gradient -> Nesterov/momentum SGD on the last global weights ->
+// new global weights saved to the backup -> live weights = lerp(new global, local, alpha). The reference runs these
+// as four passes over the fragment (set grads, outer_optimizer.step(), save_parameters, _merge_parameters:
+// /root/reference/torchft/local_sgd.py:339-384,445-475); here every element is read and written once.
+template <typename T>
+__global__ void __launch_bounds__(512, 2) diloco_outer_kernel(T* __restrict__ param, T* __restrict__ original,
+                                                               const T* __restrict__ grad, float* __restrict__ mom,
+                                                               size_t n, float lr, float mu, int nesterov, float alpha,
+                                                               const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  constexpr int N = Pack<T>::N;
+  const size_t nvec = n / N;
+  for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+    const Vec16 gv = ld_stream(grad + v * N), ov = ld_stream(original + v * N), lv = ld_stream(param + v * N);
+    float g[N], o[N], l[N], b[N];
+    Pack<T>::unpack(gv, g);
+    Pack<T>::unpack(ov, o);
+    Pack<T>::unpack(lv, l);
+#pragma unroll
+    for (int i = 0; i < N; i += 4) Pack<float>::unpack(ld_stream(mom + v * N + i), b + i);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float step = g[i];
+      if (mu != 0.f) {
+        b[i] = mu * b[i] + g[i];
+        step = nesterov ? g[i] + mu * b[i] : b[i];
+      }
+      o[i] -= lr * step;
+      l[i] = o[i] + alpha * (l[i] - o[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i += 4) st_stream(mom + v * N + i, Pack<float>::pack(b + i));
+    st_stream(original + v * N, Pack<T>::pack(o));
+    st_stream(param + v * N, Pack<T>::pack(l));
+  }
+  if (blockIdx.x == 0) {
+    for (size_t k = nvec * N + threadIdx.x; k < n; k += blockDim.x) {
+      const float g = float(grad[k]);
+      float b = mom[k], step = g;
+      if (mu != 0.f) {
+        b = mu * b + g;
+        step = nesterov ? g + mu * b : b;
+        mom[k] = b;
+      }
+      const float o = float(original[k]) - lr * step;
+      original[k] = T(o);
+      param[k] = T(o + alpha * (float(param[k]) - o));
+    }
+  }
+}
+
 // sum of squares of a bf16 buffer -> out[0] (+=), for grad-norm clipping
 __global__ void __launch_bounds__(512) sumsq_kernel(const bf16* __restrict__ g, size_t n,
                                                     float* __restrict__ out) {
@@ -502,6 +553,27 @@ void adamw_launch(void* p, float* master, float* m, float* v, const void* g, siz
   // 1184 -> 0.89, 2368 -> 0.92 of measured HBM bandwidth: many short CTAs keep both resident slots of
   // every SM refilled. max_blocks > 0 overrides.
   adamw_kernel<<<grid_for(n / 8 + 1, 512, max_blocks > 0 ? max_blocks : 148 * 16), 512, 0, s>>>(a);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void diloco_outer_launch(void* param, void* original, const void* grad, float* mom, size_t n, int dtype, float lr,
+                         float mu, int nesterov, float alpha, const int* gate, cudaStream_t s) {
+  const int grid = grid_for(n / 4 + 1, 512, 148 * 16);
+  switch (dtype) {
+    case kF32:
+      diloco_outer_kernel<float><<<grid, 512, 0, s>>>((float*)param, (float*)original, (const float*)grad, mom, n, lr, mu,
+                                                      nesterov, alpha, gate);
+      break;
+    case kBF16:
+      diloco_outer_kernel<bf16><<<grid, 512, 0, s>>>((bf16*)param, (bf16*)original, (const bf16*)grad, mom, n, lr, mu,
+                                                     nesterov, alpha, gate);
+      break;
+    case kF16:
+      diloco_outer_kernel<__half><<<grid, 512, 0, s>>>((__half*)param, (__half*)original, (const __half*)grad, mom, n, lr,
+                                                       mu, nesterov, alpha, gate);
+      break;
+    default: throw std::runtime_error("diloco_outer: unsupported dtype");
+  }
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 

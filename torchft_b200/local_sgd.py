@@ -204,7 +204,84 @@ class _StreamingDiLoCoFragment:
             self.original_parameters[name] = t
         # persistent pseudo-gradient buffers in NVLink-symmetric memory (zero-copy / in-switch all-reduce)
         self._symm_flat: Dict[Tuple[torch.dtype, torch.device], torch.Tensor] = {}
-        self._alloc_symmetric_buffers()
+        # B200 fast path (see _try_flat_mode): the fragment is ONE flat buffer end to end
+        self._flat_param: Optional[torch.Tensor] = None
+        self._flat_orig: Optional[torch.Tensor] = None
+        self._flat_grad: Optional[torch.Tensor] = None
+        self._flat_mom: Optional[torch.Tensor] = None
+        if not self._try_flat_mode():
+            self._alloc_symmetric_buffers()
+
+    # ------------------------------------------------------------------ flat fast path
+    def _try_flat_mode(self) -> bool:
+        """When the fragment's parameters are adjacent views of one CUDA buffer (``models.llama.FlatParams`` lays models
+        out like that), the backup lives on the same GPU and the outer optimizer is momentum/Nesterov SGD, a sync is two
+        launches over flat buffers instead of per-parameter copies + four passes:
+
+        * ``prepare_sync``: ``allreduce_delta(flat_grad, flat_original, flat_param)`` -- ``original - local``, fp8
+          quantisation, exchange, reduction and dequantisation in ONE kernel straight on symmetric memory;
+        * ``perform_sync``: ``diloco_outer`` -- outer SGD step, save of the new global weights and the alpha merge in
+          ONE kernel (reference: set grads + ``outer_optimizer.step()`` + ``save_parameters`` + ``_merge_parameters``,
+          local_sgd.py:339-384,445-475).
+
+        The outer optimizer object then only supplies hyper-parameters (lr schedulers keep working); its momentum lives in
+        ``self._flat_mom`` (fp32) and travels with heals under ``"outer_momentum"``.
+        """
+        if os.environ.get("TORCHFT_B200_DILOCO_FLAT", "1") == "0" or not self._params:
+            return False
+        opt = self._outer_optimizer
+        if type(opt) is not optim.SGD or len(opt.param_groups) != 1:
+            return False
+        g = opt.param_groups[0]
+        if g.get("weight_decay", 0) != 0 or g.get("dampening", 0) != 0 or g.get("maximize", False):
+            return False
+        ps = [p.data for p in self._params]
+        dev, dt = ps[0].device, ps[0].dtype
+        if dev.type != "cuda" or dt not in (torch.float32, torch.bfloat16, torch.float16):
+            return False
+        if self._backup_device is None or torch.device(self._backup_device).type != "cuda":
+            return False
+        if any(_is_dtensor(p) or p.device != dev or p.dtype != dt or not p.is_contiguous() for p in ps):
+            return False
+        if {id(q) for q in g["params"]} != {id(q) for q in self._params}:
+            return False
+        es = ps[0].element_size()
+        store = ps[0].untyped_storage()
+        if any(p.untyped_storage().data_ptr() != store.data_ptr() for p in ps):
+            return False
+        order = sorted(range(len(ps)), key=lambda i: ps[i].data_ptr())
+        lo = ps[order[0]].data_ptr()
+        end = lo
+        for i in order:
+            if ps[i].data_ptr() < end or ps[i].data_ptr() - end > 4096 * es:  # overlapping or far apart: not one flat buffer
+                return False
+            end = ps[i].data_ptr() + ps[i].numel() * es
+        if lo % 16:
+            return False
+        span = ((end - lo) // es + 7) // 8 * 8
+        if (lo - store.data_ptr()) + span * es > store.nbytes():
+            span = (end - lo) // es
+        alloc = getattr(self._manager, "alloc_symmetric", None)
+        if alloc is None or not self._manager.supports_fused_delta():
+            return False
+        try:
+            buf = alloc(f"diloco_f{self._fragment_id}_flat", span * es)
+            if self.should_quantize:  # scratch for the Q8G wire format: the whole fragment in one launch
+                alloc(f"diloco_f{self._fragment_id}_q8", span * 516 // 512 + 16 * 516 + 4096)
+        except Exception:  # noqa: BLE001 - group already configured etc.
+            logger.exception("flat DiLoCo path unavailable (symmetric memory); using the generic path")
+            return False
+        if not isinstance(buf, torch.Tensor) or buf.device != dev:
+            return False
+        self._flat_param = torch.empty(0, dtype=dt, device=dev).set_(store, (lo - store.data_ptr()) // es, (span,))
+        self._flat_grad = buf.view(dt)[:span]
+        self._flat_grad.zero_()
+        self._flat_orig = torch.empty(span, dtype=dt, device=dev)
+        self._flat_mom = torch.zeros(span, dtype=torch.float32, device=dev)
+        for name, p in zip(self._names, self._params):
+            off = (p.data.data_ptr() - lo) // es
+            self.original_parameters[name] = self._flat_orig[off: off + p.numel()].view(p.shape)
+        return True
 
     def _group_sizes(self) -> Dict[Tuple[torch.dtype, torch.device], List[int]]:
         groups: Dict[Tuple[torch.dtype, torch.device], List[int]] = {}
@@ -246,18 +323,27 @@ class _StreamingDiLoCoFragment:
                 if name in self.original_parameters:
                     self.original_parameters[name].copy_(value)
             self._outer_optimizer.load_state_dict(state_dict["outer_optimizer"])
+            if self._flat_mom is not None and "outer_momentum" in state_dict:
+                self._flat_mom.copy_(state_dict["outer_momentum"])
 
         def save_fn() -> Dict[str, Dict[str, torch.Tensor]]:
-            return {
+            out = {
                 "outer_optimizer": self._outer_optimizer.state_dict(),
                 "original_parameters": {n: extract_local_tensor(t) for n, t in self.original_parameters.items()},
             }
+            if self._flat_mom is not None:
+                out["outer_momentum"] = self._flat_mom
+            return out
 
         self._manager.register_state_dict_fn(key, load_fn, save_fn)
 
     # ------------------------------------------------------------ param copies
     @torch.profiler.record_function("torchft::local_sgd::save_parameters")
     def save_parameters(self) -> None:
+        if self._flat_orig is not None:
+            with torch.no_grad():
+                self._flat_orig.copy_(self._flat_param)
+            return
         with torch.no_grad():
             for name, p in zip(self._names, self._params):
                 self.original_parameters[name].copy_(_local_view(p.data), non_blocking=True)
@@ -269,6 +355,10 @@ class _StreamingDiLoCoFragment:
 
     @torch.profiler.record_function("torchft::local_sgd::restore_parameters")
     def restore_parameters(self) -> None:
+        if self._flat_orig is not None:
+            with torch.no_grad():
+                self._flat_param.copy_(self._flat_orig)
+            return
         with torch.no_grad():
             for name, p in zip(self._names, self._params):
                 _assign(p, self.original_parameters[name], non_blocking=False)
@@ -292,6 +382,11 @@ class _StreamingDiLoCoFragment:
         """
         self._grads = {}
         self._flat_grads = []
+        if self._flat_grad is not None:
+            assert self._flat_orig is not None and self._flat_param is not None
+            self._allreduce_work.append(self._manager.allreduce_delta(
+                self._flat_grad, self._flat_orig, self._flat_param, should_quantize=self.should_quantize))
+            return
         groups = self._group_sizes()
         locals_ = [_local_view(p.data) for p in self._params]
         fused = self.should_quantize and self._manager.supports_fused_delta()
@@ -374,6 +469,9 @@ class _StreamingDiLoCoFragment:
                 self._stop_event.record()
         self.wait()
 
+        if self._flat_grad is not None:
+            return self._perform_sync_flat()
+
         self._save_local_parameters()  # needed for the alpha merge
         self.restore_parameters()      # back to the last global weights
         should_commit = self._manager.should_commit()
@@ -386,6 +484,24 @@ class _StreamingDiLoCoFragment:
         self._clear_local_parameters()
         self._grads = {}
         self._flat_grads = []
+        return should_commit
+
+
+    def _perform_sync_flat(self) -> bool:
+        """Commit decision, then ONE kernel: outer step on the last global weights, save them, merge with local."""
+        from torchft_b200.ops import _native
+
+        assert self._flat_param is not None and self._flat_orig is not None and self._flat_mom is not None
+        should_commit = self._manager.should_commit()
+        with torch.no_grad():
+            if should_commit:
+                g = self._outer_optimizer.param_groups[0]
+                _native.load().diloco_outer(
+                    self._flat_param.data_ptr(), self._flat_orig.data_ptr(), self._flat_grad.data_ptr(), self._flat_mom.data_ptr(),
+                    self._flat_param.numel(), _native.dtype_code(self._flat_param), float(g["lr"]), float(g.get("momentum", 0.0)),
+                    bool(g.get("nesterov", False)), float(self._fragment_update_alpha), 0, _native.stream_ptr())
+            else:
+                self._flat_param.copy_(self._flat_orig)  # the window is discarded: back to the last global weights
         return should_commit
 
 

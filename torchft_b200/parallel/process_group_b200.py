@@ -46,7 +46,18 @@ from torchft_b200.process_group import (
 logger = logging.getLogger(__name__)
 
 _NATIVE_DTYPES = (torch.float32, torch.bfloat16, torch.float16)
-_OPS = {ReduceOp.SUM: _native.OP_SUM, ReduceOp.MAX: _native.OP_MAX, ReduceOp.MIN: _native.OP_MIN}
+
+
+def _native_op(op: Any) -> Optional[tuple]:
+    """``(kernel op code, is_avg)`` for reduce ops the kernels implement, else ``None``. Compared with ``==``:
+    ``opts.reduceOp`` is a ``ReduceOp`` OBJECT whose hash differs from the ``ReduceOp.SUM`` enum member, so a dict
+    lookup silently misses (and used to send plain SUM all-reduces to the NCCL sidecar)."""
+    for member, code in ((ReduceOp.SUM, _native.OP_SUM), (ReduceOp.MAX, _native.OP_MAX), (ReduceOp.MIN, _native.OP_MIN)):
+        if op == member:
+            return code, False
+    if op == ReduceOp.AVG:
+        return _native.OP_SUM, True
+    return None
 
 
 class StreamWork(Work):
@@ -250,10 +261,9 @@ class ProcessGroupB200(ProcessGroup):
         return self._launch(lambda s: self._comm.q8_reduce_scatter_(out, inp, slice_elems, scale=scale, stream=s), out)
 
     def allreduce(self, tensors: List[torch.Tensor], opts: Any) -> Work:
-        op = _reduce_op(opts)
-        if all(self._native_ok(t) for t in tensors) and (op in _OPS or op == ReduceOp.AVG):
-            scale = 1.0 / self._world if op == ReduceOp.AVG else 1.0
-            code = _OPS.get(op, _native.OP_SUM)
+        kind = _native_op(_reduce_op(opts))
+        if kind is not None and all(self._native_ok(t) for t in tensors):
+            code, scale = kind[0], (1.0 / self._world if kind[1] else 1.0)
 
             def run(s: torch.cuda.Stream) -> None:
                 for t in tensors:
@@ -322,9 +332,9 @@ class ProcessGroupB200(ProcessGroup):
         return self._get_sidecar().allgather_into_tensor_coalesced(output_tensors, input_tensors, opts)
 
     def _reduce_kind(self, opts: Any, tensors: List[torch.Tensor]) -> Optional[tuple]:
-        op = _reduce_op(opts)
-        if (op in _OPS or op == ReduceOp.AVG) and all(self._raw_ok(t) and t.dtype in _NATIVE_DTYPES for t in tensors):
-            return _OPS.get(op, _native.OP_SUM), (1.0 / self._world if op == ReduceOp.AVG else 1.0)
+        kind = _native_op(_reduce_op(opts))
+        if kind is not None and all(self._raw_ok(t) and t.dtype in _NATIVE_DTYPES for t in tensors):
+            return kind[0], (1.0 / self._world if kind[1] else 1.0)
         return None
 
     def reduce_scatter(self, output_tensors: List[torch.Tensor], input_tensors: List[List[torch.Tensor]], opts: Any) -> Work:

@@ -484,6 +484,18 @@ class SymmetricComm:
                     out.copy_(res)
                 return
             es = a.element_size()
+            # a dedicated scratch segment ("<name>_q8", allocated by the caller before the first quorum) that holds the
+            # whole message in wire format: ONE launch instead of one per 256 MB staging chunk
+            need = self._K.q8_buffer_bytes(a.numel(), self._world)
+            for name, seg in self._segments.items():
+                if name.endswith("_q8") and seg.nbytes >= need:
+                    n = a.numel()
+                    blocks = max(4, min(self._q8_max_blocks, (n // 512) // 32 + 1))
+                    K.q8_allreduce(self._tables[name], self._status, 0, a.data_ptr(), b.data_ptr() if b is not None else 0,
+                                   out.data_ptr(), n, dt, scale, self._next_flag(), _CH_Q8, contribute, blocks,
+                                   self._barrier_mode, sp)
+                    self.launches += 1
+                    return
             # elements per launch such that the Q8G buffer fits in staging
             per = (self._staging_usable * 512 // 516) // (512 * self._world) * (512 * self._world) - 512 * self._world
             fo, fa = out.view(-1), a.view(-1)

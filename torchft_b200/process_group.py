@@ -521,6 +521,60 @@ class ProcessGroupNCCL(ProcessGroupWrapper):
         return "torchft-nccl"
 
 
+# --------------------------------------------------------------------------- xccl
+class ProcessGroupXCCL(ProcessGroupWrapper):
+    """Reconfigurable XCCL group for Intel XPUs (reference: process_group.py:894-1002).
+
+    API-parity component only: this package's compute and collective kernels are sm_100a CUDA and nothing here is
+    exercised on a B200. The wrapper follows the reference's shape -- per-quorum communicator over the prefixed store,
+    user-space timeouts that call ``abort`` -- and needs a torch build with XCCL (``torch.distributed.is_xccl_available()``);
+    ``configure`` raises a clear error otherwise.
+    """
+
+    def __init__(self, timeout: timedelta = timedelta(seconds=60.0)) -> None:
+        super().__init__(timeout)
+        self._errored: Optional[Exception] = None
+
+    @staticmethod
+    def available() -> bool:
+        fn = getattr(dist, "is_xccl_available", None)
+        return bool(fn and fn()) and hasattr(torch, "xpu") and torch.xpu.is_available()
+
+    def _wrap_work(self, work: Work, opts: Any) -> Work:
+        return _WorkAcceleratorTimeout(self, work, self._timeout)
+
+    def _create_pg(self, store: Store, rank: int, world_size: int) -> BaseProcessGroup:
+        if not self.available():
+            raise RuntimeError("ProcessGroupXCCL needs a PyTorch build with XCCL and an Intel XPU; on NVIDIA B200 use "
+                               "ProcessGroupB200 (native NVLink kernels) or ProcessGroupNCCL")
+        from torch.distributed import ProcessGroupXCCL as _XCCL  # type: ignore[attr-defined]
+
+        self._errored = None
+        opts = _XCCL.Options()
+        if self._global_ranks and hasattr(opts, "global_ranks_in_group"):
+            opts.global_ranks_in_group = self._global_ranks
+        if self._group_rank is not None and self._group_world_size and hasattr(opts, "group_name"):
+            opts.group_name = f"torchft_quorum_{self._quorum_id}_rank_{self._group_rank % self._group_world_size}"
+        pg = BaseProcessGroup(store, rank, world_size)
+        pg._set_default_backend(BaseProcessGroup.BackendType.XCCL)
+        backend = _XCCL(store, rank, world_size, opts)
+        backend._set_sequence_number_for_group()
+        pg._register_backend(torch.device("xpu"), BaseProcessGroup.BackendType.XCCL, backend)
+        return pg
+
+    def abort(self, errored: bool = True) -> None:
+        self._errored = RuntimeError("aborted")
+        super().abort(errored=errored)
+
+    def errored(self) -> Optional[Exception]:
+        if hasattr(torch, "xpu") and torch.xpu.is_available():
+            torch.xpu.synchronize()
+        return self._errored
+
+    def getBackendName(self) -> str:
+        return "torchft-xccl"
+
+
 # -------------------------------------------------------------------------- dummy
 class ProcessGroupDummy(ProcessGroup):
     """World-size-1 group: every collective copies input to output and completes.
