@@ -234,7 +234,26 @@ def main() -> None:
     ap.add_argument("--ac", default=None, help="activation checkpointing: none|full (default: auto)")
     ap.add_argument("--no-baseline-arm", action="store_true",
                     help="native arm only: skip the in-process run of the reference-equivalent NCCL arm")
-    args = ap.parse_args()
+    ap.add_argument("--config", default="hsdp", choices=["hsdp", "diloco", "heal"],
+                    help="BASELINE.json config: hsdp (2, default: the flagship step), diloco (3: Llama-3-8B, outer step every "
+                         "100, fused fp8 outer all-reduce; launch under torchrun), heal (4: kill a replica group at step 50, "
+                         "rejoin at 80; launch WITHOUT torchrun, it spawns one process per GPU)")
+    args, extra = ap.parse_known_args()
+
+    if args.config != "hsdp":
+        import runpy
+
+        script = {"diloco": "diloco_bench.py", "heal": "heal_bench.py"}[args.config]
+        if args.config == "diloco":
+            argv = ["--model", args.model, "--seq", str(args.seq), "--sync-every", "100", "--outer-steps", "1",
+                    "--out", "gpurun_out/bench_diloco.json"] + (["--quantize"] if args.quantize or "--no-quantize" not in extra else [])
+        else:
+            argv = ["--gpus", str(args.gpus), "--model", args.model, "--seq", str(args.seq), "--kill-at", "50", "--rejoin-at", "80",
+                    "--steps", "100", "--out", "gpurun_out/bench_heal.json"]
+        argv += [x for x in extra if x != "--no-quantize"]
+        sys.argv = [os.path.join(ROOT, "bench", script)] + argv
+        runpy.run_path(sys.argv[0], run_name="__main__")
+        return
 
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:  # under torchrun only rank 0 reports

@@ -30,6 +30,7 @@ def main() -> None:
     ap.add_argument("--sync-every", type=int, default=20)
     ap.add_argument("--outer-steps", type=int, default=3)
     ap.add_argument("--quantize", action="store_true")
+    ap.add_argument("--no-flat", action="store_true", help="generic per-parameter DiLoCo path instead of the flat fast path")
     ap.add_argument("--out", default="gpurun_out/diloco_bench.json")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -43,7 +44,7 @@ def main() -> None:
     from torchft_b200.bench_utils import loopback
     from torchft_b200.coordination import LighthouseServer
     from torchft_b200.local_sgd import DiLoCo
-    from torchft_b200.models.llama import CONFIGS, Llama
+    from torchft_b200.models.llama import CONFIGS, FlatParams, Llama
 
     lh = None
     addr = [None]
@@ -54,6 +55,9 @@ def main() -> None:
 
     cfg = CONFIGS[a.model]
     model = Llama(cfg, device=dev)
+    if not a.no_flat:
+        # one flat weight buffer: DiLoCo then syncs with ONE fused delta all-reduce + ONE fused outer-step kernel
+        FlatParams(model)
     model.init_weights(0)
     inner = torch.optim.AdamW(model.parameters(), lr=3e-4, fused=True)
     outer = torch.optim.SGD(model.parameters(), lr=0.7, momentum=0.9, nesterov=True)
@@ -88,7 +92,8 @@ def main() -> None:
                "quantize": a.quantize, "tokens_per_s": round(world * a.seq * a.sync_every / float(t[0]) * 1e3, 1),
                "inner_step_ms": round(float(t[1]), 2), "sync_step_ms": round(float(t[2]), 2),
                "outer_sync_overhead_ms": round(float(t[2] - t[1]), 2), "outer_steps_committed": manager.current_step(),
-               "pseudo_grad_bytes": nparam * 2}
+               "pseudo_grad_bytes": nparam * 2, "flat_fast_path": not a.no_flat,
+               "link_time_ms_at_770GBps": round((nparam * (1 if a.quantize else 2)) * 2 * (world - 1) / world / 770e6, 2)}
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
         with open(a.out, "a") as f:
             f.write(json.dumps(res) + "\n")

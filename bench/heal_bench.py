@@ -52,7 +52,11 @@ def worker(args: argparse.Namespace) -> None:
         rec = {"event": "step", "replica": args.replica, "t": time.time(), "ms": (time.time() - t0) * 1e3,
                "step_before": before, "step_after": m.current_step(), "participants": m.num_participants(),
                "quorum_id": m._quorum_id, "loss": loss, "committed": m.current_step() > before,
-               "psum": float(trainer.flat.param[: 1 << 22].float().abs().sum().item())}
+               "psum": int(trainer.flat.param.view(torch.int16).sum(dtype=torch.int64).item())}  # exact checksum of ALL weights
+        if getattr(trainer, "zopt", None) is not None:
+            rec["z1_pulled_bytes"] = trainer.zopt.pulled_bytes
+            rec["z1_lost_elements"] = trainer.zopt.lost_elements
+            rec["z1_t"] = trainer.zopt.t
         if getattr(tr, "last_recv_bytes", 0):
             rec["heal_bytes"] = tr.last_recv_bytes
             rec["heal_ms"] = tr.last_recv_ms
@@ -182,10 +186,14 @@ def main() -> None:
         # replicas must hold bit-identical weights at equal committed steps (oracle of the
         # reference's integration tests: state_dict equality after injected failures)
         "weights_match_at_common_steps": _weights_match(sv, vc),
+        "zero1": {"victim_reshard_pulled_gb": round(max((e.get("z1_pulled_bytes", 0) for e in vc), default=0) / 1e9, 2),
+                  "survivor_reshard_pulled_gb": round(max((e.get("z1_pulled_bytes", 0) for e in sv), default=0) / 1e9, 2),
+                  "lost_elements": max((e.get("z1_lost_elements", 0) for e in sv + vc), default=0)},
     }
     with open(args.out, "w") as f:
         json.dump(res, f, indent=1)
-    print("HEAL_BENCH " + json.dumps({k: res[k] for k in ("steady_ms_before_kill", "drop", "heal", "final_steps", "survivor_rc", "victim_rc")}))
+    print("HEAL_BENCH " + json.dumps({k: res[k] for k in ("steady_ms_before_kill", "drop", "heal", "final_steps", "survivor_rc", "victim_rc",
+                                                               "weights_match_at_common_steps", "zero1")}))
 
 
 if __name__ == "__main__":

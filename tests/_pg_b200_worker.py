@@ -89,7 +89,7 @@ def main() -> None:
     pg.reduce_scatter([out], [ins], ro).wait()
     torch.cuda.synchronize()
     check("reduce_scatter", bool((out == sum(r * 10 + rank for r in range(world))).all()), got=out[:2].tolist())
-    big = torch.arange(world * 1000, device=dev, dtype=torch.bfloat16) % 7 * (rank + 1)
+    big = ((torch.arange(world * 1000, device=dev) % 7) * (rank + 1)).to(torch.bfloat16)
     out2 = torch.empty(1000, device=dev, dtype=torch.bfloat16)
     ro.reduceOp = ReduceOp.AVG
     pg.reduce_scatter_tensor_coalesced([out2], [big], ro).wait()

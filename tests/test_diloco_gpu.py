@@ -26,7 +26,7 @@ def _run(flat: bool, alpha: float, quantize: bool, nesterov: bool):
     lh = local_lighthouse()
     store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
     cfg = CONFIGS["llama3_tiny"]
-    model = Llama(cfg, device=dev, dtype=torch.float32)
+    model = Llama(cfg, device=dev)  # bf16: the fused model kernels are bf16-only
     FlatParams(model)
     model.init_weights(3)
     pg = ProcessGroupB200(timeout=timedelta(seconds=20), device=dev)
@@ -62,5 +62,7 @@ def _run(flat: bool, alpha: float, quantize: bool, nesterov: bool):
 def test_flat_diloco_matches_generic_path(alpha, quantize, nesterov):
     pg_, og_ = _run(False, alpha, quantize, nesterov)
     pf_, of_ = _run(True, alpha, quantize, nesterov)
-    torch.testing.assert_close(pf_, pg_, rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(of_, og_, rtol=1e-4, atol=1e-5)
+    # bf16 weights; the generic path keeps its momentum in bf16 (torch SGD), the fused kernel in fp32
+    for got, want in ((pf_, pg_), (of_, og_)):
+        diff = (got.float() - want.float()).abs()
+        assert float(diff.max()) <= 2e-2 and float(diff.mean()) <= 2e-3, (float(diff.max()), float(diff.mean()))

@@ -1,0 +1,144 @@
+"""Fault-tolerant HSDP trainer: FSDP2 shards INSIDE a replica group, torchft_b200 ACROSS groups.
+
+BASELINE.json config 2 ("4 replica groups x 2-GPU FSDP shards"), wired the way the reference composes it
+(/root/reference/torchft/fsdp_test.py:57-72, README.md:62-69): ``fully_shard`` over the group's own mesh,
+``set_all_reduce_hook`` so every reduce-scattered gradient shard is averaged across replica groups through a
+``ManagedProcessGroup`` (-> ``Manager.allreduce`` -> the fused NVLink all-reduce kernel on ``ProcessGroupB200``, with
+the 1/num_participants scale and the zero contribution of healing groups inside the kernel), one Manager per rank,
+one ManagerServer per group, ``should_commit`` as the AND-barrier over the group's ranks.
+
+All ranks of ALL groups may live in one ``torchrun`` world (how ``bench.py --shards S`` is launched): rank ``r`` is
+shard ``r % S`` of group ``r // S``; intra-group collectives (FSDP all-gather / reduce-scatter) run on plain NCCL
+sub-groups, which is outside the fault-tolerance scope exactly as in the reference.
+"""
+
+from __future__ import annotations
+
+import os
+from datetime import timedelta
+from typing import Any, Optional
+
+import torch
+import torch.distributed as dist
+from torch.distributed import TCPStore
+
+
+class HSDPTrainer:
+    """Llama over ``groups x shards`` GPUs.
+
+    Args:
+        model: config name in ``models.llama.CONFIGS``
+        lighthouse_addr: address of a running Lighthouse
+        shards: FSDP degree inside a replica group (the torchrun world is cut into consecutive blocks of this size)
+        backend: ``"b200"`` (native cross-replica kernels) or ``"nccl"`` (reference-equivalent arm)
+    """
+
+    def __init__(self, model: str, lighthouse_addr: str, shards: int, backend: str = "b200", lr: float = 3e-4,
+                 timeout: timedelta = timedelta(seconds=120), device: Optional[torch.device] = None, seed: int = 0,
+                 replica_prefix: str = "hsdp") -> None:
+        from torch.distributed.device_mesh import init_device_mesh
+        from torch.distributed.fsdp import MixedPrecisionPolicy, fully_shard
+
+        from torchft_b200 import ManagedProcessGroup, Manager, Optimizer
+        from torchft_b200.models.llama import CONFIGS, Llama
+
+        assert dist.is_initialized(), "init the NCCL world first (torchrun)"
+        rank, world = dist.get_rank(), dist.get_world_size()
+        assert world % shards == 0
+        self.groups, self.shards = world // shards, shards
+        self.group, self.group_rank = rank // shards, rank % shards
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.cfg = CONFIGS[model]
+        mesh = init_device_mesh("cuda", (self.groups, shards), mesh_dim_names=("replicate", "shard"))
+        shard_mesh = mesh["shard"]
+        shard_pg = shard_mesh.get_group()
+
+        # the group's store: hosted by its shard rank 0, port shared over the (NCCL) shard group
+        port = [0]
+        if self.group_rank == 0:
+            self._store = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
+            port = [self._store.port]
+        dist.broadcast_object_list(port, group=shard_pg, group_src=0)
+
+        # fp32 master parameters sharded by FSDP2, bf16 compute copies, fp32 gradient reduction
+        torch.manual_seed(seed)
+        m = Llama(self.cfg, device=self.device, dtype=torch.float32)
+        m.init_weights(seed)
+        mp = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)
+        for blk in m.layers:
+            fully_shard(blk, mesh=shard_mesh, mp_policy=mp)
+        fully_shard(m, mesh=shard_mesh, mp_policy=mp)
+        self.model = m
+
+        if backend == "b200":
+            from torchft_b200.parallel.process_group_b200 import ProcessGroupB200
+
+            self.pg: Any = ProcessGroupB200(timeout=timeout, device=self.device)
+        else:
+            from torchft_b200.process_group import ProcessGroupNCCL
+
+            self.pg = ProcessGroupNCCL(timeout=timeout)
+        self.manager = Manager(pg=self.pg, load_state_dict=None, state_dict=None, min_replica_size=self.groups,
+                               timeout=timeout, quorum_timeout=timeout, connect_timeout=timeout, rank=self.group_rank,
+                               world_size=shards, store_addr="127.0.0.1", store_port=int(port[0]),
+                               lighthouse_addr=lighthouse_addr, replica_id=f"{replica_prefix}_{self.group}", init_sync=False)
+        self.manager.register_state_dict_fn("model", lambda sd: None, lambda: {})
+        replicate = ManagedProcessGroup(self.manager)
+
+        def cross_replica(shard_grad: torch.Tensor) -> None:
+            # FSDP2 hands over the reduce-scattered gradient shard of one parameter group, on its reduce stream
+            replicate.allreduce([shard_grad], dist.ReduceOp.AVG).wait()
+
+        for mod in m.modules():
+            if hasattr(mod, "set_all_reduce_hook"):
+                mod.set_all_reduce_hook(cross_replica)
+        self.inner = torch.optim.AdamW(m.parameters(), lr=lr, betas=(0.9, 0.95), weight_decay=0.1, fused=True)
+        self.optim = Optimizer(self.manager, self.inner)
+        self._tok: Optional[torch.Tensor] = None
+        self._tgt: Optional[torch.Tensor] = None
+        self._loss_host: Optional[torch.Tensor] = None
+        self._loss_event: Optional[torch.cuda.Event] = None
+        self.zero1 = False
+        self.zopt = None
+
+    def step_device(self, tokens: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        self.optim.zero_grad(set_to_none=True)   # start_quorum (async)
+        loss = self.model(tokens, targets)
+        loss.backward()                          # FSDP reduce-scatter + cross-replica hook per block, overlapped
+        self.optim.step()                        # should_commit (AND over the group's ranks), then AdamW on the shards
+        return loss
+
+    def join(self) -> None:
+        pass
+
+    def _stage(self, tokens_cpu: torch.Tensor, targets_cpu: torch.Tensor) -> None:
+        if self._tok is None or self._tok.shape != tokens_cpu.shape:
+            self._tok = torch.empty(tokens_cpu.shape, dtype=torch.int64, device=self.device)
+            self._tgt = torch.empty(tokens_cpu.shape, dtype=torch.int64, device=self.device)
+        assert self._tgt is not None
+        self._tok.copy_(tokens_cpu, non_blocking=True)
+        self._tgt.copy_(targets_cpu, non_blocking=True)
+
+    def step_async(self, tokens_cpu: torch.Tensor, targets_cpu: torch.Tensor) -> Optional[float]:
+        prev = None
+        if self._loss_event is not None:
+            self._loss_event.synchronize()
+            prev = float(self._loss_host[0])  # type: ignore[index]
+        self._stage(tokens_cpu, targets_cpu)
+        loss = self.step_device(self._tok, self._tgt)  # type: ignore[arg-type]
+        if self._loss_host is None:
+            self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+            self._loss_event = torch.cuda.Event()
+        self._loss_host.copy_(loss.detach().float().reshape(1), non_blocking=True)
+        self._loss_event.record()  # type: ignore[union-attr]
+        return prev
+
+    def last_loss(self) -> Optional[float]:
+        if self._loss_event is None:
+            return None
+        self._loss_event.synchronize()
+        return float(self._loss_host[0])  # type: ignore[index]
+
+    def shutdown(self) -> None:
+        self.manager.shutdown(wait=False)
+        self.pg.shutdown()
