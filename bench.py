@@ -126,6 +126,11 @@ def run_arm(impl: str, args, rank: int, world: int, local: int, lh_addr: str) ->
     backend = "b200" if impl == "native" else "nccl"
 
     def build(ac):
+        if args.shards > 1:
+            from torchft_b200.parallel.hsdp import HSDPTrainer
+
+            return HSDPTrainer(args.model, lh_addr, args.shards, backend=backend, timeout=timedelta(seconds=120), device=dev,
+                               replica_prefix=impl)
         return FaultTolerantTrainer(args.model, lh_addr, replica_id=f"{impl}_{rank}", min_replica_size=world,
                                     backend=backend, bucket_mb=args.bucket_mb, should_quantize=args.quantize,
                                     activation_checkpoint=ac, timeout=timedelta(seconds=120), device=dev,
@@ -231,6 +236,9 @@ def main() -> None:
     ap.add_argument("--bucket-mb", type=float, default=512.0)
     ap.add_argument("--quantize", action="store_true")
     ap.add_argument("--replication", type=int, default=2, help="FT-ZeRO-1: holders per slice of optimizer state")
+    ap.add_argument("--shards", type=int, default=1,
+                    help="FSDP2 shard degree INSIDE a replica group (BASELINE config 2 headline: --gpus 8 --shards 2 = 4 groups x 2 "
+                         "shards); default 1 = every GPU is a replica group holding the full model (fits in 180 GB)")
     ap.add_argument("--ac", default=None, help="activation checkpointing: none|full (default: auto)")
     ap.add_argument("--no-baseline-arm", action="store_true",
                     help="native arm only: skip the in-process run of the reference-equivalent NCCL arm")
@@ -279,10 +287,14 @@ def main() -> None:
 
     # bootstrap only (publish the lighthouse address, reduce timings): gloo on CPU
     lighthouse = None
+    assert world % args.shards == 0, "--shards must divide the number of GPUs"
     if world > 1:
-        dist.init_process_group("gloo", timeout=timedelta(seconds=300))
+        if args.shards > 1:  # FSDP's intra-group collectives need NCCL; everything else here only uses the CPU side
+            dist.init_process_group("cpu:gloo,cuda:nccl", timeout=timedelta(seconds=300), device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo", timeout=timedelta(seconds=300))
         if rank == 0:
-            lighthouse = LighthouseServer(bind="[::]:0", min_replicas=world, join_timeout_ms=60000)
+            lighthouse = LighthouseServer(bind="[::]:0", min_replicas=world // args.shards, join_timeout_ms=60000)
             addr = [lighthouse.address()]
         else:
             addr = [None]
@@ -330,12 +342,15 @@ def main() -> None:
                 "params_b": round(cfg.num_params() / 1e9, 3),
                 "global_batch": B * world,
                 "seq_len": S,
-                "parallelism": (f"ft-ddp over {world} replica group(s) x 1 GPU (HSDP shard degree 1)"
+                "parallelism": (f"ft-hsdp: {world // args.shards} replica groups x {args.shards}-GPU FSDP2 shards (cross-replica "
+                                f"all-reduce of every reduce-scattered shard through ManagedProcessGroup)") if args.shards > 1 else
+                               (f"ft-ddp over {world} replica group(s) x 1 GPU (HSDP shard degree 1)"
                                 + (f" + FT-ZeRO-1: optimizer state partitioned over the replicas, k={min(args.replication, world)} holders per slice"
                                    if res["zero1"] else "")),
                 "optimizer": ("AdamW (fp32 master/m/v) on the held 1/N slices, gated by the device-side commit verdict, fused with the "
                               "all-gather of the new bf16 weights; one launch per transformer block under the next forward") if res["zero1"]
-                             else "AdamW (fp32 master/m/v), full on every replica, applied only after the host-synchronous should_commit",
+                             else ("torch AdamW (fused) on FSDP2 fp32 parameter shards, applied only after should_commit" if args.shards > 1
+                                   else "AdamW (fp32 master/m/v), full on every replica, applied only after the host-synchronous should_commit"),
                 "activation_checkpoint": res["ac"],
                 "grad_reduction": ("fused reduce-scatter kernel per block over NVLink peer memory (1/N scale, bf16 cast, zero "
                                    "contribution, buddy push), zero-copy symmetric buffers, overlapped with backward") if res["zero1"]

@@ -52,7 +52,7 @@ def worker(args: argparse.Namespace) -> None:
         rec = {"event": "step", "replica": args.replica, "t": time.time(), "ms": (time.time() - t0) * 1e3,
                "step_before": before, "step_after": m.current_step(), "participants": m.num_participants(),
                "quorum_id": m._quorum_id, "loss": loss, "committed": m.current_step() > before,
-               "psum": int(trainer.flat.param.view(torch.int16).sum(dtype=torch.int64).item())}  # exact checksum of ALL weights
+               "psum": _checksum(trainer.flat.param)}  # exact checksum of ALL weights
         if getattr(trainer, "zopt", None) is not None:
             rec["z1_pulled_bytes"] = trainer.zopt.pulled_bytes
             rec["z1_lost_elements"] = trainer.zopt.lost_elements
@@ -64,6 +64,14 @@ def worker(args: argparse.Namespace) -> None:
         log.write(json.dumps(rec) + "\n")
     log.write(json.dumps({"event": "done", "replica": args.replica, "t": time.time()}) + "\n")
     trainer.shutdown()
+
+
+def _checksum(t) -> int:
+    """Exact integer checksum of a bf16 buffer, in 256M-element chunks (a one-shot int64 reduction would need 4x the memory)."""
+    import torch
+
+    v = t.view(torch.int16)
+    return sum(int(v[i: i + (1 << 28)].sum(dtype=torch.int64).item()) for i in range(0, v.numel(), 1 << 28))
 
 
 def _weights_match(a: list, b: list):

@@ -33,7 +33,7 @@ from torchft_b200.parallel.symm_mem import SymmetricComm  # noqa: E402
 HP = (3e-4, 0.9, 0.95, 1e-8, 0.1)
 
 
-def run_rank(comm, nelem, k, blocks, iters, warmup, sync, reduce_max):
+def run_rank(comm, nelem, k, rs_blocks, upd_blocks, iters, warmup, sync, reduce_max):
     dev = comm.device
     grad = comm.segment("z1_grad")[: nelem * 2].view(torch.bfloat16)
     grad.normal_()
@@ -43,10 +43,10 @@ def run_rank(comm, nelem, k, blocks, iters, warmup, sync, reduce_max):
     gate = torch.ones(2, dtype=torch.int32, device=dev)
 
     def rs():
-        comm.zero1_reduce_scatter_("z1_grad", 0, nelem, 1.0 / max(comm.world, 1), True, k, blocks)
+        comm.zero1_reduce_scatter_("z1_grad", 0, nelem, 1.0 / max(comm.world, 1), True, k, rs_blocks)
 
     def upd():
-        comm.zero1_update_("z1_param", 0, grad.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(), nelem, HP, gate, k, 0, blocks)
+        comm.zero1_update_("z1_param", 0, grad.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(), nelem, HP, gate, k, 0, upd_blocks)
 
     out = {}
     for name, fn in (("reduce_scatter", rs), ("adamw_allgather", upd)):
@@ -69,7 +69,8 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--mb", type=float, default=436.0, help="unit size in MB of bf16 gradients (one Llama-3-8B block = 436 MB)")
     ap.add_argument("--replication", type=int, default=2)
-    ap.add_argument("--blocks", type=int, default=64)
+    ap.add_argument("--rs-blocks", type=int, default=128)
+    ap.add_argument("--upd-blocks", type=int, default=2368)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--virtual", type=int, default=0, help="emulate this many ranks on ONE GPU (presignalled; for ncu)")
@@ -83,7 +84,7 @@ def main() -> None:
         comms = SymmetricComm.virtual_world(a.virtual, {"z1_grad": S, "z1_param": S}, presignal=True)
         res = {"mode": f"virtual{a.virtual}", "unit_mb": S / 2**20}
         for c in comms[:1]:  # rank 0's kernels are representative; every rank does the same work
-            res.update(run_rank(c, nelem, a.replication, a.blocks, a.iters, a.warmup, torch.cuda.synchronize, lambda x: x))
+            res.update(run_rank(c, nelem, a.replication, a.rs_blocks, a.upd_blocks, a.iters, a.warmup, torch.cuda.synchronize, lambda x: x))
         print("ZERO1_BENCH " + json.dumps(res), flush=True)
         return
 
@@ -109,9 +110,9 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    res = {"world": world, "unit_mb": round(S / 2**20, 1), "replication": min(a.replication, world), "blocks": a.blocks,
+    res = {"world": world, "unit_mb": round(S / 2**20, 1), "replication": min(a.replication, world), "rs_blocks": a.rs_blocks, "upd_blocks": a.upd_blocks,
            "mode": comm._mode, "nvls": bool(comm._mc)}
-    t = run_rank(comm, nelem, a.replication, a.blocks, a.iters, a.warmup, sync, reduce_max)
+    t = run_rank(comm, nelem, a.replication, a.rs_blocks, a.upd_blocks, a.iters, a.warmup, sync, reduce_max)
     k = min(a.replication, world)
     link = 770.0  # GB/s per direction per GPU (B200_PROFILING.md)
     hbm = 6571.0
@@ -120,7 +121,7 @@ def main() -> None:
         res["reduce_scatter"] = {"ms": round(t["reduce_scatter"], 3), "nvlink_in_gb": round(inb / 1e9, 3),
                                  "in_gbps": round(inb / t["reduce_scatter"] / 1e6, 1),
                                  "frac_of_770": round(inb / t["reduce_scatter"] / 1e6 / link, 3)}
-    outb = (world - 1) / world * S
+    outb = max(0, world - k) / world * S  # holders compute their own copy: the primary pushes to W - k ranks
     hbm_b = 28.0 * nelem * k / world
     floor_ms = max(outb / (link * 1e6), hbm_b / (hbm * 1e6)) if world > 1 else hbm_b / (hbm * 1e6)
     res["adamw_allgather"] = {"ms": round(t["adamw_allgather"], 3), "nvlink_out_gb": round(outb / 1e9, 3),

@@ -7,6 +7,10 @@ import pytest
 # share a hardware work queue would order them falsely (a kernel queued behind one that waits for it). More queues
 # (must be set before CUDA initialises) make that impossible for the handful of streams the tests use.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# With lazy module loading the FIRST launch of a kernel may have to wait for the context to go idle; a kernel of another
+# emulated rank that is already spinning for it would then never see it start. Real ranks are separate processes with their
+# own contexts; the single-process harness loads everything up front instead.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

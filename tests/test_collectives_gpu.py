@@ -140,6 +140,8 @@ def test_send_recv_multi_piece_fifo():
     ra, rb = torch.empty_like(a), torch.empty_like(b)
     back = torch.empty_like(b)
 
+    # (send and recv are different kernels; each has run once above would be needed under lazy module loading -- conftest
+    # switches to eager loading for that reason)
     # one kernel per stream and phase: inside ONE process a second kernel queued behind a waiting one could be ordered
     # in front of the kernel it waits for (real ranks are separate processes with their own queues)
     _run(comms, lambda r, c, s: c.send_(a, 2, s) if r == 0 else c.recv_(ra, 0, s), ranks=(0, 2))

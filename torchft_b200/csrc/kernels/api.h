@@ -24,18 +24,18 @@ void allreduce_nvls_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, 
                            int barrier_mode, cudaStream_t stream);
 
 // zero1.cu -------------------------------------------------------------------
-// FT-ZeRO-1: reduce-scatter (+ buddy push), device-side commit verdict, gated AdamW fused with the
-// all-gather of the new bf16 weights. mc_base != nullptr selects the NVLS (multimem) data path.
-void zero1_reduce_scatter_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, size_t off, size_t nelem,
-                                 float scale, uint64_t flag, int channel, int contribute, int replication,
-                                 int blocks, int threads, int barrier_mode, cudaStream_t stream);
+// FT-ZeRO-1: one-CTA handshake (flag exchange with every peer, result mirrored to a device word), sync-free
+// reduce-scatter body (+ buddy push), device-side commit verdict, sync-free gated AdamW fused with the all-gather of the
+// new bf16 weights. mc_base != nullptr selects the NVLS (multimem) data path.
+void zero1_handshake_launch(const PeerTable& pt, StatusBlock* st, int* ok_out, uint64_t flag, int channel, int release,
+                            int barrier_mode, cudaStream_t stream);
+void zero1_reduce_launch(const PeerTable& pt, const int* ok, void* mc_base, size_t off, size_t nelem, float scale,
+                         int replication, int blocks, int threads, cudaStream_t stream);
 void zero1_commit_launch(const PeerTable& pt, StatusBlock* st, int* gate, uint64_t flag, uint32_t seq, int channel,
                          int host_ok, int exchange, cudaStream_t stream);
-void zero1_adamw_allgather_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, const int* gate, size_t poff,
-                                  const void* grad, float* master, float* m, float* v, size_t nelem, float lr,
-                                  float b1, float b2, float eps, float wd, uint64_t flag, int channel,
-                                  int replication, int mode, int blocks, int threads, int barrier_mode,
-                                  cudaStream_t stream);
+void zero1_update_launch(const PeerTable& pt, void* mc_base, const int* gate, size_t poff, const void* grad, float* master,
+                         float* m, float* v, size_t nelem, float lr, float b1, float b2, float eps, float wd,
+                         int replication, int mode, int blocks, int threads, cudaStream_t stream);
 
 // collectives.cu --------------------------------------------------------------
 // push exchange = all-gather / broadcast / all-to-all over staging slots (arrays have pt.world entries);
@@ -95,5 +95,8 @@ void diloco_outer_launch(void* param, void* original, const void* grad, float* m
 void sumsq_launch(const void* g, size_t n, float* out, cudaStream_t s);
 void heal_copy_launch(const void* table_dev, int nentries, size_t total_chunks, size_t chunk_bytes,
                       int blocks, cudaStream_t s);
+
+void heal_copy_bulk_launch(const void* table_dev, int nentries, size_t total_chunks, size_t chunk_bytes, int blocks,
+                           cudaStream_t s);
 
 }  // namespace tft

@@ -219,16 +219,21 @@ PYBIND11_MODULE(_K, m) {
       py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
 
   m.def(
-      "zero1_reduce_scatter",
-      [](const PeerTableH& pt, const Status& st, uintptr_t mc_base, size_t off, size_t nelem, float scale,
-         uint64_t flag, int channel, bool contribute, int replication, int blocks, int threads, int barrier_mode,
+      "zero1_handshake",
+      [](const PeerTableH& pt, const Status& st, uintptr_t ok_out, uint64_t flag, int channel, bool release, int barrier_mode,
          uintptr_t stream) {
-        zero1_reduce_scatter_launch(pt.pt, st.dev(), P<void>(mc_base), off, nelem, scale, flag, channel,
-                                    contribute ? 1 : 0, replication, blocks, threads, barrier_mode, S(stream));
+        zero1_handshake_launch(pt.pt, st.dev(), P<int>(ok_out), flag, channel, release ? 1 : 0, barrier_mode, S(stream));
       },
-      py::arg("pt"), py::arg("status"), py::arg("mc_base"), py::arg("off"), py::arg("nelem"), py::arg("scale"),
-      py::arg("flag"), py::arg("channel"), py::arg("contribute"), py::arg("replication"), py::arg("blocks"),
-      py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
+      py::arg("pt"), py::arg("status"), py::arg("ok_out"), py::arg("flag"), py::arg("channel"), py::arg("release"),
+      py::arg("barrier_mode"), py::arg("stream"));
+  m.def(
+      "zero1_reduce",
+      [](const PeerTableH& pt, uintptr_t ok, uintptr_t mc_base, size_t off, size_t nelem, float scale, int replication,
+         int blocks, int threads, uintptr_t stream) {
+        zero1_reduce_launch(pt.pt, P<const int>(ok), P<void>(mc_base), off, nelem, scale, replication, blocks, threads, S(stream));
+      },
+      py::arg("pt"), py::arg("ok"), py::arg("mc_base"), py::arg("off"), py::arg("nelem"), py::arg("scale"),
+      py::arg("replication"), py::arg("blocks"), py::arg("threads"), py::arg("stream"));
   m.def(
       "zero1_commit",
       [](const PeerTableH& pt, const Status& st, uintptr_t gate, uint64_t flag, uint32_t seq, int channel,
@@ -239,19 +244,16 @@ PYBIND11_MODULE(_K, m) {
       py::arg("pt"), py::arg("status"), py::arg("gate"), py::arg("flag"), py::arg("seq"), py::arg("channel"),
       py::arg("host_ok"), py::arg("exchange"), py::arg("stream"));
   m.def(
-      "zero1_adamw_allgather",
-      [](const PeerTableH& pt, const Status& st, uintptr_t mc_base, uintptr_t gate, size_t poff, uintptr_t grad,
-         uintptr_t master, uintptr_t mm, uintptr_t v, size_t nelem, float lr, float b1, float b2, float eps,
-         float wd, uint64_t flag, int channel, int replication, int mode, int blocks, int threads,
-         int barrier_mode, uintptr_t stream) {
-        zero1_adamw_allgather_launch(pt.pt, st.dev(), P<void>(mc_base), P<const int>(gate), poff, P<void>(grad),
-                                     P<float>(master), P<float>(mm), P<float>(v), nelem, lr, b1, b2, eps, wd,
-                                     flag, channel, replication, mode, blocks, threads, barrier_mode, S(stream));
+      "zero1_update",
+      [](const PeerTableH& pt, uintptr_t mc_base, uintptr_t gate, size_t poff, uintptr_t grad, uintptr_t master, uintptr_t mm,
+         uintptr_t v, size_t nelem, float lr, float b1, float b2, float eps, float wd, int replication, int mode,
+         int blocks, int threads, uintptr_t stream) {
+        zero1_update_launch(pt.pt, P<void>(mc_base), P<const int>(gate), poff, P<void>(grad), P<float>(master), P<float>(mm),
+                            P<float>(v), nelem, lr, b1, b2, eps, wd, replication, mode, blocks, threads, S(stream));
       },
-      py::arg("pt"), py::arg("status"), py::arg("mc_base"), py::arg("gate"), py::arg("poff"), py::arg("grad"),
-      py::arg("master"), py::arg("m"), py::arg("v"), py::arg("nelem"), py::arg("lr"), py::arg("b1"),
-      py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("flag"), py::arg("channel"), py::arg("replication"),
-      py::arg("mode"), py::arg("blocks"), py::arg("threads"), py::arg("barrier_mode"), py::arg("stream"));
+      py::arg("pt"), py::arg("mc_base"), py::arg("gate"), py::arg("poff"), py::arg("grad"), py::arg("master"),
+      py::arg("m"), py::arg("v"), py::arg("nelem"), py::arg("lr"), py::arg("b1"), py::arg("b2"), py::arg("eps"),
+      py::arg("wd"), py::arg("replication"), py::arg("mode"), py::arg("blocks"), py::arg("threads"), py::arg("stream"));
 
   m.def(
       "push_exchange",
@@ -383,6 +385,9 @@ PYBIND11_MODULE(_K, m) {
      py::arg("mu"), py::arg("nesterov"), py::arg("alpha"), py::arg("gate"), py::arg("stream"));
   m.def("sumsq", [](uintptr_t g, size_t n, uintptr_t out, uintptr_t s) {
     sumsq_launch(P<void>(g), n, P<float>(out), S(s));
+  });
+  m.def("heal_copy_bulk", [](uintptr_t table_dev, int nentries, size_t total_chunks, size_t chunk_bytes, int blocks, uintptr_t s) {
+    heal_copy_bulk_launch(P<void>(table_dev), nentries, total_chunks, chunk_bytes, blocks, S(s));
   });
   m.def("heal_copy", [](uintptr_t table_dev, int nentries, size_t total_chunks, size_t chunk_bytes,
                         int blocks, uintptr_t s) {

@@ -167,8 +167,8 @@ __device__ __forceinline__ bool wait_flag(const uint64_t* flag, uint64_t expecte
 // `mode` selects the memory-ordering recipe (tuned on hardware, bench/comm_tune.py):
 //   0  per-peer thread: [fence.sc.sys if release] st.release.sys ; poll ld.acquire.sys
 //   1  per-peer thread: st.release.sys ; poll ld.relaxed.sys ; fence.acq_rel.sys
-//   2  thread 0: [fence.acq_rel.sys if release] ; per-peer st.relaxed.sys ; poll relaxed ;
-//      thread 0: [fence.acq_rel.sys if acquire]          (<= 2 system fences per CTA)
+//   2  per-peer thread (all in warp 0): [fence.acq_rel.sys if release] ; st.relaxed.sys ; poll relaxed ;
+//      [fence.acq_rel.sys if acquire]        (<= 2 warp-wide system fences per CTA, each in program order with its flag access)
 //   3  like 2 but the flag is published with red.release.sys (atomic max) so the
 //      store cannot linger in a write-combining path
 __device__ __forceinline__ bool wait_flag_acquire(const uint64_t* flag, uint64_t expected,
@@ -222,23 +222,26 @@ __device__ __forceinline__ bool block_barrier(const PeerTable& pt, int ch, uint6
     }
     return __syncthreads_and(ok) != 0;
   }
-  if (release) {
-    if (t == 0) fence_acq_rel_sys();
-    __syncthreads();
-  }
-  if (t < pt.world && t != pt.rank) {
-    uint64_t* remote = &pt.pads[t]->sig[ch][blockIdx.x][pt.rank];
-    if (mode == 3)
-      red_max_release_sys(remote, flag);
-    else
-      st_relaxed_sys(remote, flag);
-    ok = wait_flag(&pt.pads[pt.rank]->sig[ch][blockIdx.x][t], flag, st, t, pt.timeout_ns) ? 1 : 0;
+  // The signalling threads t < world all sit in warp 0, so "every signalling thread fences" costs one warp-wide fence
+  // instruction -- the same as thread 0 alone -- but gives each flag store / flag poll its own fence IN PROGRAM ORDER,
+  // i.e. a well-formed release (fence; st.relaxed) and acquire (ld.relaxed; fence) pattern under the PTX memory model.
+  // The CTA's data accesses are ordered around them by the __syncthreads() that opened this function (and the
+  // __syncthreads_and() below): bar.sync is morally strong at CTA scope and the fences are cumulative.
+  const bool signaller = t < pt.world && t != pt.rank;
+  if (t < 32) {
+    if (signaller) {
+      if (release) fence_acq_rel_sys();
+      uint64_t* remote = &pt.pads[t]->sig[ch][blockIdx.x][pt.rank];
+      if (mode == 3)
+        red_max_release_sys(remote, flag);
+      else
+        st_relaxed_sys(remote, flag);
+      ok = wait_flag(&pt.pads[pt.rank]->sig[ch][blockIdx.x][t], flag, st, t, pt.timeout_ns) ? 1 : 0;
+    }
+    __syncwarp();  // reconverge the pollers so the acquire fence is ONE warp-wide instruction again
+    if (signaller && acquire) fence_acq_rel_sys();
   }
   ok = __syncthreads_and(ok);
-  if (acquire) {
-    if (t == 0) fence_acq_rel_sys();
-    __syncthreads();
-  }
   return ok != 0;
 }
 

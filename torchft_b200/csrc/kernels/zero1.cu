@@ -5,26 +5,33 @@
 // (/root/reference/torchft/manager.py:466-478, /root/reference/torchft/optim.py:52-55). Here the
 // replicated dimension also partitions the optimizer:
 //
-//   backward :  zero1_reduce_scatter_kernel   per unit (layer), overlapped with backward.
-//               Rank r reduces slice r of the unit straight out of every peer's HBM (P2P loads, or
-//               ONE multimem.ld_reduce per 16 B when the segment is bound to an NVLS multicast
-//               object), fp32 accumulate in fixed rank order, 1/num_participants scale and bf16
-//               cast in registers, zero contribution of healing/spare replicas, and writes the
-//               reduced slice to itself AND to its k-1 buddies (k-way replicated ownership, so a
-//               replica that dies never holds the only copy of a shard of optimizer state).
-//   commit   :  zero1_commit_kernel           ONE tiny kernel replaces the host sync + RPC: every
-//               rank publishes "my step is clean" (no latched error, enough participants) into
-//               its peers' signal pads, the verdict is the AND over the quorum, written to a
-//               device gate word, a device step counter and a host-mapped ring the Manager reads
-//               lazily at the next start_quorum.
-//   update   :  zero1_adamw_allgather_kernel  per unit in forward order, gated on the device word.
-//               AdamW (fp32 master/m/v) on the slices this rank holds; the PRIMARY holder packs
-//               the new weights to bf16 and stores them into every replica's parameter buffer
-//               (P2P stores, or ONE multimem.st per 16 B) -- the all-gather is the epilogue of the
-//               update, tile by tile, and the next forward overlaps it unit by unit.
+//   backward :  per unit (transformer block), on the comm stream, overlapped with backward:
+//                 handshake            "my gradients of this unit are complete" <-> every peer's same message
+//                 zero1_reduce_kernel  rank r reduces slice r straight out of every peer's HBM (P2P loads, or ONE
+//                                      multimem.ld_reduce per 16 B when the segment is bound to an NVLS multicast
+//                                      object), fp32 accumulate in fixed rank order, 1/num_participants scale and
+//                                      bf16 cast in registers, and writes the reduced slice to itself AND to its
+//                                      k-1 buddies (k-way replicated ownership: a replica that dies never holds
+//                                      the only copy of a shard of optimizer state)
+//                 handshake            "my pushes have landed / I am done reading yours"
+//   commit   :  zero1_commit_kernel    ONE tiny kernel replaces the host sync + RPC: every rank publishes "my step is
+//                                      clean" into its peers' signal pads, the verdict is the AND over the quorum,
+//                                      written to a device gate word, a device step counter and a host-mapped ring
+//                                      the Manager reads lazily at the next start_quorum.
+//   update   :  per unit in forward order, on the optimizer stream, gated on the device word:
+//                 zero1_update_kernel  AdamW (fp32 master/m/v) on the slices this rank holds, new bf16 weights
+//                                      written locally; the PRIMARY holder also stores them into the parameter
+//                                      buffer of every replica that does not hold the slice (P2P stores, or ONE
+//                                      multimem.st per 16 B) -- the all-gather is the epilogue of the update
+//                 handshake            "my weight pushes have landed" (skipped when every rank holds everything)
 //
-// Per rank and step this moves the same NVLink bytes as a two-shot all-reduce but divides the
-// 28 B/param optimizer HBM traffic (and the state a replica must hold) by N/k.
+// The two big kernels contain NO inter-rank synchronisation at all: any grid size, no co-residency requirement, no
+// SM held by a spinning CTA while peers are skewed, profilable stand-alone. Ordering comes from the one-CTA handshake
+// kernels around them (bounded, abortable spins; epoch-tagged flags; error latched in the status block and mirrored
+// in a device word the big kernels test so a failed handshake turns them into no-ops).
+//
+// Per rank and step this moves the same NVLink bytes as a two-shot all-reduce but divides the 28 B/param optimizer
+// HBM traffic (and the state a replica must hold) by N/k.
 #include <stdexcept>
 #include <string>
 
@@ -62,108 +69,109 @@ struct Geo {
   __device__ size_t hi(int s) const { return min((size_t)(s + 1) * slice, nvec); }
 };
 
+// ---------------------------------------------------------------------------
+// Handshake: one CTA, one flag exchange with every peer. `ok_out` (device) receives 1/0 so the
+// sync-free kernels that follow on the same stream can turn themselves into no-ops after a failure.
+// ---------------------------------------------------------------------------
+struct HsArgs {
+  PeerTable pt;
+  StatusBlock* st;
+  int* ok_out;
+  uint64_t flag;     // consumes flag+1
+  int channel;
+  int release;       // this rank wrote peer-visible data in an earlier kernel of this stream
+  int barrier_mode;
+};
+
+__global__ void __launch_bounds__(32, 1) zero1_handshake_kernel(HsArgs a) {
+  const bool ok = block_barrier(a.pt, a.channel, a.flag + 1, a.st, a.release != 0, /*acquire=*/true, a.barrier_mode);
+  if (threadIdx.x == 0) *a.ok_out = ok ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// Reduce-scatter body (no synchronisation).
+// ---------------------------------------------------------------------------
 struct RSArgs {
   PeerTable pt;       // data[] = every rank's gradient segment
-  StatusBlock* st;
+  const int* ok;      // result of the handshake in front of this kernel
   char* mc;           // multicast VA of the gradient segment (nullptr = P2P loads)
   size_t off;         // byte offset of the unit inside the segment
   size_t nelem;       // elements in the unit (multiple of 8)
   float scale;
-  uint64_t flag;      // consumes flag+1, flag+2
-  int channel;
-  int contribute;
   int replication;    // k
-  int barrier_mode;
 };
 
 template <int W, bool NVLS>
-__global__ void __launch_bounds__(512, 1) zero1_reduce_scatter_kernel(RSArgs a) {
+__global__ void __launch_bounds__(512, 1) zero1_reduce_kernel(RSArgs a) {
+  if (*a.ok == 0) return;
   const int rank = a.pt.rank;
   const Geo g(a.nelem, W);
-  bf16* mine = reinterpret_cast<bf16*>(reinterpret_cast<char*>(a.pt.data[rank]) + a.off);
-
-  if (!a.contribute) {
-    // healing / spare replica: its gradients must count as zeros (reference manager.py:441-442);
-    // zero them in place instead of a separate zero_() pass. Block b zeroes chunk b of every slice.
-    const size_t chunk = (g.slice + gridDim.x - 1) / gridDim.x;
-    for (int s = 0; s < W; ++s) {
-      const size_t lo = g.lo(s) + blockIdx.x * chunk, hi = min(lo + chunk, g.hi(s));
-      for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) st_stream(mine + v * 8, Vec16{0, 0, 0, 0});
-    }
+  const bf16* src[W];
+  bf16* dst[W];
+#pragma unroll
+  for (int p = 0; p < W; ++p) {
+    src[p] = reinterpret_cast<const bf16*>(reinterpret_cast<const char*>(a.pt.data[p]) + a.off);
+    dst[p] = reinterpret_cast<bf16*>(reinterpret_cast<char*>(a.pt.data[(rank + p) % W]) + a.off);
   }
-  if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/!a.contribute, /*acquire=*/false, a.barrier_mode))
-    return;
-
-  {
-    const bf16* src[W];
-    bf16* dst[W];
+  const char* mcbase = a.mc + a.off;
+  const int k = min(a.replication, W);
+  const size_t lo = g.lo(rank), hi = g.hi(rank);
+  constexpr int U = NVLS ? 8 : ((W >= 8) ? 2 : (W >= 3 ? 4 : 8));
+  const size_t stride = (size_t)gridDim.x * blockDim.x * U;
+  for (size_t base = lo + (size_t)blockIdx.x * blockDim.x * U; base < hi; base += stride) {
+    if constexpr (NVLS) {
+      Vec16 r[U];
 #pragma unroll
-    for (int p = 0; p < W; ++p) {
-      src[p] = reinterpret_cast<const bf16*>(reinterpret_cast<const char*>(a.pt.data[p]) + a.off);
-      dst[p] = reinterpret_cast<bf16*>(reinterpret_cast<char*>(a.pt.data[(rank + p) % W]) + a.off);
-    }
-    const char* mcbase = a.mc + a.off;
-    const int k = min(a.replication, W);
-    const size_t chunk = (g.slice + gridDim.x - 1) / gridDim.x;
-    const size_t lo = g.lo(rank) + blockIdx.x * chunk, hi = min(lo + chunk, g.hi(rank));
-    constexpr int U = NVLS ? 8 : ((W >= 8) ? 2 : (W >= 3 ? 4 : 8));
-    for (size_t base = lo; base < hi; base += (size_t)blockDim.x * U) {
-      if constexpr (NVLS) {
-        Vec16 r[U];
+      for (int u = 0; u < U; ++u) {
+        const size_t v = base + threadIdx.x + (size_t)u * blockDim.x;
+        if (v < hi) r[u] = mm_ld_reduce_bf16(mcbase + v * 16);
+      }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const size_t v = base + threadIdx.x + (size_t)u * blockDim.x;
-          if (v < hi) r[u] = mm_ld_reduce_bf16(mcbase + v * 16);
+      for (int u = 0; u < U; ++u) {
+        const size_t v = base + threadIdx.x + (size_t)u * blockDim.x;
+        if (v < hi) {
+          float f[8];
+          P8::unpack(r[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] *= a.scale;
+          const Vec16 out = P8::pack(f);
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+            if (j < k) st_stream(dst[j] + v * 8, out);
         }
+      }
+    } else {
+      Vec16 in[U][W];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const size_t v = base + threadIdx.x + (size_t)u * blockDim.x;
-          if (v < hi) {
-            float f[8];
-            P8::unpack(r[u], f);
+      for (int u = 0; u < U; ++u) {
+        const size_t v = base + threadIdx.x + (size_t)u * blockDim.x;
+        if (v < hi) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] *= a.scale;
-            const Vec16 out = P8::pack(f);
-#pragma unroll
-            for (int j = 0; j < W; ++j)
-              if (j < k) st_stream(dst[j] + v * 8, out);
-          }
+          for (int p = 0; p < W; ++p) in[u][p] = ld_stream(src[p] + v * 8);
         }
-      } else {
-        Vec16 in[U][W];
+      }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const size_t v = base + threadIdx.x + (size_t)u * blockDim.x;
-          if (v < hi) {
+      for (int u = 0; u < U; ++u) {
+        const size_t v = base + threadIdx.x + (size_t)u * blockDim.x;
+        if (v < hi) {
+          float acc[8], f[8];
+          P8::unpack(in[u][0], acc);
 #pragma unroll
-            for (int p = 0; p < W; ++p) in[u][p] = ld_stream(src[p] + v * 8);
+          for (int p = 1; p < W; ++p) {
+            P8::unpack(in[u][p], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
           }
-        }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const size_t v = base + threadIdx.x + (size_t)u * blockDim.x;
-          if (v < hi) {
-            float acc[8], f[8];
-            P8::unpack(in[u][0], acc);
+          for (int i = 0; i < 8; ++i) acc[i] *= a.scale;
+          const Vec16 out = P8::pack(acc);
 #pragma unroll
-            for (int p = 1; p < W; ++p) {
-              P8::unpack(in[u][p], f);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] += f[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] *= a.scale;
-            const Vec16 out = P8::pack(acc);
-#pragma unroll
-            for (int j = 0; j < W; ++j)
-              if (j < k) st_stream(dst[j] + v * 8, out);
-          }
+          for (int j = 0; j < W; ++j)
+            if (j < k) st_stream(dst[j] + v * 8, out);
         }
       }
     }
   }
-  // buddies read the pushed slice in a LATER kernel (the gated update): release only
-  block_barrier(a.pt, a.channel, a.flag + 2, a.st, /*release=*/true, /*acquire=*/false, a.barrier_mode);
 }
 
 // ---------------------------------------------------------------------------
@@ -221,11 +229,10 @@ __global__ void __launch_bounds__(32, 1) zero1_commit_kernel(CommitArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// Gated AdamW on the held slices + all-gather of the new bf16 weights.
+// Gated AdamW on the held slices + all-gather of the new bf16 weights (no synchronisation).
 // ---------------------------------------------------------------------------
 struct UpdArgs {
   PeerTable pt;        // data[] = every rank's PARAMETER segment
-  StatusBlock* st;
   char* mc;            // multicast VA of the parameter segment (nullptr = P2P stores)
   const int* gate;     // gate[0] verdict, gate[1] step count (already incremented for this step)
   size_t poff;         // byte offset of the unit inside the parameter segment
@@ -235,15 +242,12 @@ struct UpdArgs {
   float* v;
   size_t nelem;
   float lr, b1, b2, eps, wd;
-  uint64_t flag;       // consumes flag+1
-  int channel;
   int replication;
-  int mode;            // 0 = gated update + push, 1 = refresh (push bf16(master) of primary slices, ungated)
-  int barrier_mode;
+  int mode;            // 0 = gated update + push, 1 = refresh (re-broadcast bf16(master) of the primary slice, ungated)
 };
 
 template <int W, bool NVLS>
-__global__ void __launch_bounds__(512, (W == 1) ? 2 : 1) zero1_adamw_allgather_kernel(UpdArgs a) {
+__global__ void __launch_bounds__(512, 2) zero1_update_kernel(UpdArgs a) {
   if (a.mode == 0 && a.gate[0] == 0) return;  // uniform over the grid AND (unanimous verdict) over the quorum
   const int rank = a.pt.rank;
   const Geo g(a.nelem, W);
@@ -253,17 +257,20 @@ __global__ void __launch_bounds__(512, (W == 1) ? 2 : 1) zero1_adamw_allgather_k
   const float step_size = a.lr / bc1;
   const float inv_bc2_sqrt = rsqrtf(bc2);
   const float decay = 1.f - a.lr * a.wd;
+  // dst[0] = this rank; dst[j] = rank + j. Ranks rank+1 .. rank+k-1 hold the primary slice too and compute the same
+  // bits themselves, so the primary only pushes to dst[k .. W-1] (mode 0). A refresh pushes to everybody.
   bf16* dst[W];
 #pragma unroll
   for (int p = 0; p < W; ++p)
     dst[p] = reinterpret_cast<bf16*>(reinterpret_cast<char*>(a.pt.data[(rank + p) % W]) + a.poff);
   char* mcbase = a.mc + a.poff;
-  const size_t chunk = (g.slice + gridDim.x - 1) / gridDim.x;
+  const int first_push = a.mode == 0 ? k : 1;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
 
   for (int j = 0; j < (a.mode == 0 ? k : 1); ++j) {
     const int s = (rank - j + W) % W;  // j = 0: primary slice, j > 0: slices this rank backs up
-    const size_t lo = g.lo(s) + blockIdx.x * chunk, hi = min(lo + chunk, g.hi(s));
-    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+    const size_t lo = g.lo(s), hi = g.hi(s);
+    for (size_t v = lo + tid; v < hi; v += nthreads) {
       float w[8];
       const Vec16 w0 = ld_stream(a.master + v * 8), w1 = ld_stream(a.master + v * 8 + 4);
       if (a.mode == 0) {
@@ -296,60 +303,70 @@ __global__ void __launch_bounds__(512, (W == 1) ? 2 : 1) zero1_adamw_allgather_k
         Pack<float>::unpack(w0, w);
         Pack<float>::unpack(w1, w + 4);
       }
+      const Vec16 out = P8::pack(w);
+      st_stream(dst[0] + v * 8, out);  // every holder refreshes its own copy of the weights
       if (j == 0) {
-        const Vec16 out = P8::pack(w);
         if constexpr (NVLS) {
-          mm_st_bf16(mcbase + v * 16, out);
+          if (first_push < W) mm_st_bf16(mcbase + v * 16, out);  // the switch replicates (holders get identical bits again)
         } else {
 #pragma unroll
-          for (int p = 0; p < W; ++p) st_stream(dst[p] + v * 8, out);
+          for (int p = 1; p < W; ++p)
+            if (p >= first_push) st_stream(dst[p] + v * 8, out);
         }
       }
     }
   }
-  if (W > 1)
-    block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/true, /*acquire=*/false, a.barrier_mode);
 }
 
 template <bool NVLS>
 void launch_rs(const RSArgs& a, int blocks, int threads, cudaStream_t s) {
   switch (a.pt.world) {
-    case 2: zero1_reduce_scatter_kernel<2, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 3: zero1_reduce_scatter_kernel<3, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 4: zero1_reduce_scatter_kernel<4, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 5: zero1_reduce_scatter_kernel<5, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 6: zero1_reduce_scatter_kernel<6, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 7: zero1_reduce_scatter_kernel<7, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 8: zero1_reduce_scatter_kernel<8, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    default: throw std::runtime_error("zero1_reduce_scatter: world size must be in [2, 8]");
+    case 2: zero1_reduce_kernel<2, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 3: zero1_reduce_kernel<3, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 4: zero1_reduce_kernel<4, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 5: zero1_reduce_kernel<5, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 6: zero1_reduce_kernel<6, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 7: zero1_reduce_kernel<7, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 8: zero1_reduce_kernel<8, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    default: throw std::runtime_error("zero1_reduce: world size must be in [2, 8]");
   }
 }
 
 template <bool NVLS>
 void launch_upd(const UpdArgs& a, int blocks, int threads, cudaStream_t s) {
   switch (a.pt.world) {
-    case 1: zero1_adamw_allgather_kernel<1, false><<<blocks, threads, 0, s>>>(a); break;
-    case 2: zero1_adamw_allgather_kernel<2, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 3: zero1_adamw_allgather_kernel<3, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 4: zero1_adamw_allgather_kernel<4, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 5: zero1_adamw_allgather_kernel<5, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 6: zero1_adamw_allgather_kernel<6, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 7: zero1_adamw_allgather_kernel<7, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    case 8: zero1_adamw_allgather_kernel<8, NVLS><<<blocks, threads, 0, s>>>(a); break;
-    default: throw std::runtime_error("zero1_adamw_allgather: world size must be in [1, 8]");
+    case 1: zero1_update_kernel<1, false><<<blocks, threads, 0, s>>>(a); break;
+    case 2: zero1_update_kernel<2, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 3: zero1_update_kernel<3, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 4: zero1_update_kernel<4, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 5: zero1_update_kernel<5, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 6: zero1_update_kernel<6, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 7: zero1_update_kernel<7, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    case 8: zero1_update_kernel<8, NVLS><<<blocks, threads, 0, s>>>(a); break;
+    default: throw std::runtime_error("zero1_update: world size must be in [1, 8]");
   }
+}
+
+void check_grid(int blocks, int threads, const char* who) {
+  if (blocks < 1 || blocks > 148 * 32) throw std::runtime_error(std::string(who) + ": bad grid");
+  if (threads < 32 || threads > 512 || (threads & 31)) throw std::runtime_error(std::string(who) + ": bad block size");
 }
 
 }  // namespace
 
-void zero1_reduce_scatter_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, size_t off, size_t nelem,
-                                 float scale, uint64_t flag, int channel, int contribute, int replication,
-                                 int blocks, int threads, int barrier_mode, cudaStream_t stream) {
-  if (blocks < 1 || blocks > kMaxBlocks) throw std::runtime_error("zero1_reduce_scatter: bad grid");
-  if (threads < 32 || threads > 512 || (threads & 31)) throw std::runtime_error("zero1_reduce_scatter: bad block size");
-  if ((off & 15) || (nelem & 7)) throw std::runtime_error("zero1_reduce_scatter: unit must be 16 B aligned and a multiple of 8 elements");
-  if (replication < 1) throw std::runtime_error("zero1_reduce_scatter: replication must be >= 1");
-  RSArgs a{pt, st, reinterpret_cast<char*>(mc_base), off, nelem, scale, flag, channel, contribute, replication, barrier_mode};
+void zero1_handshake_launch(const PeerTable& pt, StatusBlock* st, int* ok_out, uint64_t flag, int channel, int release,
+                            int barrier_mode, cudaStream_t stream) {
+  HsArgs a{pt, st, ok_out, flag, channel, release, barrier_mode};
+  zero1_handshake_kernel<<<1, 32, 0, stream>>>(a);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void zero1_reduce_launch(const PeerTable& pt, const int* ok, void* mc_base, size_t off, size_t nelem, float scale,
+                         int replication, int blocks, int threads, cudaStream_t stream) {
+  check_grid(blocks, threads, "zero1_reduce");
+  if ((off & 15) || (nelem & 7)) throw std::runtime_error("zero1_reduce: unit must be 16 B aligned and a multiple of 8 elements");
+  if (replication < 1) throw std::runtime_error("zero1_reduce: replication must be >= 1");
+  RSArgs a{pt, ok, reinterpret_cast<char*>(mc_base), off, nelem, scale, replication};
   if (mc_base != nullptr)
     launch_rs<true>(a, blocks, threads, stream);
   else
@@ -364,16 +381,13 @@ void zero1_commit_launch(const PeerTable& pt, StatusBlock* st, int* gate, uint64
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 
-void zero1_adamw_allgather_launch(const PeerTable& pt, StatusBlock* st, void* mc_base, const int* gate, size_t poff,
-                                  const void* grad, float* master, float* m, float* v, size_t nelem, float lr,
-                                  float b1, float b2, float eps, float wd, uint64_t flag, int channel,
-                                  int replication, int mode, int blocks, int threads, int barrier_mode,
-                                  cudaStream_t stream) {
-  if (blocks < 1 || (pt.world > 1 && blocks > kMaxBlocks)) throw std::runtime_error("zero1_adamw_allgather: bad grid");
-  if (threads < 32 || threads > 512 || (threads & 31)) throw std::runtime_error("zero1_adamw_allgather: bad block size");
-  if ((poff & 15) || (nelem & 7)) throw std::runtime_error("zero1_adamw_allgather: unit must be 16 B aligned and a multiple of 8 elements");
-  UpdArgs a{pt, st, reinterpret_cast<char*>(mc_base), gate, poff, reinterpret_cast<const bf16*>(grad), master, m, v,
-            nelem, lr, b1, b2, eps, wd, flag, channel, replication, mode, barrier_mode};
+void zero1_update_launch(const PeerTable& pt, void* mc_base, const int* gate, size_t poff, const void* grad, float* master,
+                         float* m, float* v, size_t nelem, float lr, float b1, float b2, float eps, float wd,
+                         int replication, int mode, int blocks, int threads, cudaStream_t stream) {
+  check_grid(blocks, threads, "zero1_update");
+  if ((poff & 15) || (nelem & 7)) throw std::runtime_error("zero1_update: unit must be 16 B aligned and a multiple of 8 elements");
+  UpdArgs a{pt, reinterpret_cast<char*>(mc_base), gate, poff, reinterpret_cast<const bf16*>(grad), master, m, v,
+            nelem, lr, b1, b2, eps, wd, replication, mode};
   if (mc_base != nullptr)
     launch_upd<true>(a, blocks, threads, stream);
   else

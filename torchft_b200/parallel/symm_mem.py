@@ -127,6 +127,7 @@ class SymmetricComm:
         self._force_plan: Optional[Tuple[int, int]] = None  # (algo, blocks) override for tuning sweeps
         self.launches = 0  # native kernel launches issued (bench reports this)
         self._ptrs: Dict[str, List[int]] = {}  # segment -> mapped base pointer per quorum rank
+        self._z1_ok_buf: Optional[torch.Tensor] = None
         self._commit_seq = 0
         self._hostname = socket.gethostname()
 
@@ -676,18 +677,35 @@ class SymmetricComm:
         mc = self._mc.get(name)
         return mc[1] if (mc is not None and self._world > 1 and nbytes >= self._nvls_min) else 0
 
+    def _z1_ok(self, slot: int) -> int:
+        """Device word the handshake kernels write their outcome to (slot 0: comm stream, slot 1: optimizer stream)."""
+        if self._z1_ok_buf is None:
+            self._z1_ok_buf = torch.ones(4, dtype=torch.int32, device=self.device)
+        return self._z1_ok_buf.data_ptr() + 4 * slot
+
+    def _handshake(self, slot: int, release: bool, channel: int, sp: int) -> None:
+        self._K.zero1_handshake(self._tables["core"], self._status, self._z1_ok(slot), self._next_flag(), channel, release,
+                                self._barrier_mode, sp)
+        self.launches += 1
+
     def zero1_reduce_scatter_(self, segment: str, off: int, nelem: int, scale: float, contribute: bool,
                               replication: int, blocks: int, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Reduce-scatter ``nelem`` bf16 elements at byte offset ``off`` of ``segment`` in place: afterwards rank r
-        (and its ``replication - 1`` successors) hold the scaled sum of slice r."""
+        (and its ``replication - 1`` successors) hold the scaled sum of slice r. Three launches on ``stream``:
+        handshake ("my unit is ready") -> sync-free reduce kernel (any grid) -> handshake ("my pushes landed")."""
         with self._lock:
             if not self._configured:
                 raise RuntimeError("SymmetricComm is not configured")
-            blocks = max(1, min(blocks, self._K.MAX_BLOCKS, max(1, (nelem * 2) // (64 << 10))))
-            self._K.zero1_reduce_scatter(self._tables[segment], self._status, self._mc_base(segment, nelem * 2), off, nelem,
-                                         scale, self._next_flag(), _CH_ALLREDUCE, contribute, replication, blocks,
-                                         self._threads, self._barrier_mode, _native.stream_ptr(stream))
+            sp = _native.stream_ptr(stream)
+            if not contribute:
+                # healing / spare replica: its gradients count as zeros (reference manager.py:441-442)
+                self._K.memset_async(self._segments[segment].ptr + off, 0, nelem * 2, sp)
+            self._handshake(0, not contribute, _CH_ALLREDUCE, sp)
+            blocks = max(1, min(blocks, 148 * 32, (nelem // 8 + 511) // 512))
+            self._K.zero1_reduce(self._tables[segment], self._z1_ok(0), self._mc_base(segment, nelem * 2), off, nelem, scale,
+                                 replication, blocks, self._threads, sp)
             self.launches += 1
+            self._handshake(0, True, _CH_ALLREDUCE, sp)
 
     def zero1_commit_(self, gate: torch.Tensor, host_ok: bool, exchange: bool,
                       stream: Optional[torch.cuda.Stream] = None) -> int:
@@ -713,20 +731,20 @@ class SymmetricComm:
                       hyper: Tuple[float, float, float, float, float], gate: torch.Tensor, replication: int, mode: int,
                       blocks: int, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Gated AdamW on the held slices of one unit + all-gather of the primary slice's new bf16 weights into
-        ``segment`` on every rank (``mode`` 1: ungated re-broadcast of bf16(master), no state change)."""
+        ``segment`` on the ranks that do not hold it (``mode`` 1: ungated re-broadcast of bf16(master) to everybody, no
+        state change). A sync-free kernel (any grid) followed by one handshake when anything was pushed."""
         with self._lock:
             if not self._configured:
                 raise RuntimeError("SymmetricComm is not configured")
             lr, b1, b2, eps, wd = hyper
-            if self._world == 1:
-                blocks = max(1, min(148 * 16, (nelem // 8 + 511) // 512))
-            else:
-                blocks = max(1, min(blocks, self._K.MAX_BLOCKS, max(1, (nelem * 2) // (64 << 10))))
-            self._K.zero1_adamw_allgather(self._tables[segment], self._status, self._mc_base(segment, nelem * 2),
-                                          gate.data_ptr(), poff, grad, master, m, v, nelem, lr, b1, b2, eps, wd,
-                                          self._next_flag(), _CH_HEAL, replication, mode, blocks, self._threads,
-                                          self._barrier_mode, _native.stream_ptr(stream))
+            sp = _native.stream_ptr(stream)
+            blocks = max(1, min(blocks, 148 * 32, (nelem // 8 + 511) // 512))
+            self._K.zero1_update(self._tables[segment], self._mc_base(segment, nelem * 2), gate.data_ptr(), poff, grad, master,
+                                 m, v, nelem, lr, b1, b2, eps, wd, replication, mode, blocks, self._threads, sp)
             self.launches += 1
+            pushes = self._world > 1 and (mode == 1 or self._world > replication)
+            if pushes:
+                self._handshake(1, True, _CH_HEAL, sp)
 
     # ------------------------------------------------------------------ status
     def abort(self) -> None:

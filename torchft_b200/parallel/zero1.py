@@ -183,7 +183,10 @@ class Zero1Optimizer:
         self.layout: ShardLayout = ShardLayout(((0, numel),), self._replication)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
-        self._blocks = int(os.environ.get("TORCHFT_B200_Z1_BLOCKS", blocks or 64))
+        # the big kernels are sync-free, so their grids are free parameters: the reduce-scatter is NVLink-latency bound
+        # and shares the SMs with backward; the update is HBM-bound and likes many short CTAs (cf. the AdamW cap sweep)
+        self._rs_blocks = int(os.environ.get("TORCHFT_B200_Z1_RS_BLOCKS", 128))
+        self._upd_blocks = int(os.environ.get("TORCHFT_B200_Z1_UPD_BLOCKS", blocks or 2368))
         self.param = pg.alloc_symmetric("z1_param", numel * 2).view(torch.bfloat16)
         self.grad = pg.alloc_symmetric("z1_grad", numel * 2).view(torch.bfloat16)
         self.master = pg.alloc_symmetric("z1_master", numel * 4).view(torch.float32)
@@ -296,7 +299,7 @@ class Zero1Optimizer:
             return None
         k = self.layout.replication
         return self.pg._launch(
-            lambda s: self.comm.zero1_reduce_scatter_("z1_grad", lo * 2, hi - lo, scale, contribute, k, self._blocks, s),
+            lambda s: self.comm.zero1_reduce_scatter_("z1_grad", lo * 2, hi - lo, scale, contribute, k, self._rs_blocks, s),
             None)
 
     # -- committer protocol of Manager.commit_on_device ---------------------------------------------------------
@@ -338,7 +341,7 @@ class Zero1Optimizer:
             for mode in modes:
                 self.comm.zero1_update_("z1_param", lo * 2, self.grad.data_ptr() + lo * 2, self.master.data_ptr() + lo * 4,
                                         self.m.data_ptr() + lo * 4, self.v.data_ptr() + lo * 4, hi - lo, hp,
-                                        self.gate, k, mode, self._blocks, stream)
+                                        self.gate, k, mode, self._upd_blocks, stream)
             if events is not None:
                 events[i].record(stream)
 
