@@ -126,7 +126,31 @@ def main() -> None:
         a = torch.empty(n, dtype=torch.uint8, device=dev)
         b = torch.empty(n, dtype=torch.uint8, device=dev)
         for blocks in (32, 64, 148):
-            record(f"heal_copy_local_b{blocks}", timeit(lambda: device_copy([(a.data_ptr(), b.data_ptr(), n)], blocks=blocks), args.iters, flush), 2 * n)
+            record(f"heal_copy_local_b{blocks}", timeit(lambda: device_copy([(a.data_ptr(), b.data_ptr(), n)], blocks=blocks, bulk=False), args.iters, flush), 2 * n)
+        for blocks in (148, 296, 444):  # TMA variant: 64 KiB smem per CTA -> up to 3 CTAs per SM, 32 threads each
+            record(f"heal_copy_bulk_tma_b{blocks}", timeit(lambda: device_copy([(a.data_ptr(), b.data_ptr(), n)], blocks=blocks, bulk=True), args.iters, flush), 2 * n)
+        del a, b
+    if want("diloco_outer"):
+        n = 1 << 29
+        p = torch.randn(n, device=dev).bfloat16()
+        o = torch.randn(n, device=dev).bfloat16()
+        g = torch.randn(n, device=dev).bfloat16()
+        mom = torch.zeros(n, device=dev)
+        record("diloco_outer_bf16", timeit(lambda: K.diloco_outer(p.data_ptr(), o.data_ptr(), g.data_ptr(), mom.data_ptr(), n, 1, 0.7, 0.9, True, 0.25, 0, sp()), args.iters, flush), n * (2 * 5 + 8))
+        del p, o, g, mom
+    if want("zero1_update"):
+        # the FT-ZeRO-1 update kernel at world 1 (= plain gated AdamW through the same code path the trainer uses)
+        from datetime import timedelta
+
+        from torchft_b200.parallel.symm_mem import SymmetricComm
+
+        n = 1 << 28
+        c = SymmetricComm.virtual_world(1, {"z1_param": n * 2}, dev, timeout=timedelta(seconds=10))[0]
+        g = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+        master, m, v = (torch.zeros(n, device=dev) for _ in range(3))
+        gate = torch.ones(2, dtype=torch.int32, device=dev)
+        for cap in (296, 1184, 2368):
+            record(f"zero1_update_w1_cap{cap}", timeit(lambda: c.zero1_update_("z1_param", 0, g.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(), n, (1e-3, 0.9, 0.95, 1e-8, 0.1), gate, 1, 0, cap), args.iters, flush), n * 28)
     if args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         with open(args.out, "w") as f:

@@ -123,7 +123,12 @@ def test_pg_transport_step_mismatch():
     trs = [PGTransport(pgs[r], timedelta(seconds=5), torch.device("cpu")) for r in range(2)]
 
     def send():
-        trs[0].send_checkpoint([1], 3, make_state(3), timedelta(seconds=5))
+        # the receiver rejects the header and never posts the tensor receives: the sender's remaining sends time out,
+        # which is the expected outcome on this side (swallowed here so no stray thread exception outlives the test)
+        try:
+            trs[0].send_checkpoint([1], 3, make_state(3), timedelta(seconds=5))
+        except (RuntimeError, TimeoutError):
+            pass
 
     t = threading.Thread(target=send)
     t.start()

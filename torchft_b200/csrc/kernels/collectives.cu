@@ -184,8 +184,11 @@ struct P2PArgs {
   int channel;
 };
 
-__device__ __forceinline__ void piece_chunk(size_t piece_len, size_t* lo, size_t* hi) {
-  const size_t per = ((piece_len + kP2PBlocks - 1) / kP2PBlocks + 15) & ~size_t(15);
+// CTA b always owns the SAME byte range of the mailbox, whatever the piece length: its data-ready / ack flags then
+// order exactly the bytes it touches (a length-dependent split let CTA b of a short last piece overwrite bytes that CTA b'
+// of the receiver was still copying out of the previous piece).
+__device__ __forceinline__ void piece_chunk(size_t mailbox_bytes, size_t piece_len, size_t* lo, size_t* hi) {
+  const size_t per = ((mailbox_bytes + kP2PBlocks - 1) / kP2PBlocks + 15) & ~size_t(15);
   *lo = min((size_t)blockIdx.x * per, piece_len);
   *hi = min(*lo + per, piece_len);
 }
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(512, 1) p2p_send_kernel(P2PArgs a) {
       if (!ok_s) return;
     }
     size_t lo, hi;
-    piece_chunk(len, &lo, &hi);
+    piece_chunk(a.mailbox_bytes, len, &lo, &hi);
     if (lo < hi) copy_bytes(box + lo, a.buf + done + lo, hi - lo);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(512, 1) p2p_recv_kernel(P2PArgs a) {
     __syncthreads();
     if (!ok_s) return;
     size_t lo, hi;
-    piece_chunk(len, &lo, &hi);
+    piece_chunk(a.mailbox_bytes, len, &lo, &hi);
     if (lo < hi) copy_bytes(a.buf + done + lo, box + lo, hi - lo);
     __syncthreads();
     if (threadIdx.x == 0) {
