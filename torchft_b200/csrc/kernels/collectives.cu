@@ -121,10 +121,15 @@ __global__ void __launch_bounds__(512, 1) reduce_scatter_kernel(RSArgs a) {
   constexpr int N = Pack<T>::N;
   const int rank = a.pt.rank;
   T* mine = reinterpret_cast<T*>(reinterpret_cast<char*>(a.pt.data[rank]) + a.off);
-  if (a.user_in != nullptr) {
-    size_t lo, hi;
-    my_chunk(a.n * W * sizeof(T), &lo, &hi);
-    if (lo < hi) copy_bytes(reinterpret_cast<char*>(mine) + lo, reinterpret_cast<const char*>(a.user_in) + lo, hi - lo);
+  // CTA b owns elements [lo, hi) of EVERY slot, in the staging phase and in the reduce phase alike: the per-CTA barrier
+  // then orders exactly the bytes this CTA reads from its peers (they were staged by the peers' CTA b).
+  const size_t per = (((a.n + gridDim.x - 1) / gridDim.x) + N - 1) / N * N;
+  const size_t lo = min((size_t)blockIdx.x * per, a.n), hi = min(lo + per, a.n);
+  if (a.user_in != nullptr && lo < hi) {
+    const T* in = reinterpret_cast<const T*>(a.user_in);
+    for (int s = 0; s < W; ++s)
+      copy_bytes(reinterpret_cast<char*>(mine + (size_t)s * a.n + lo), reinterpret_cast<const char*>(in + (size_t)s * a.n + lo),
+                 (hi - lo) * sizeof(T));
   }
   if (!block_barrier(a.pt, a.channel, a.flag + 1, a.st, /*release=*/a.user_in != nullptr, /*acquire=*/false, a.barrier_mode)) return;
   {
@@ -134,27 +139,34 @@ __global__ void __launch_bounds__(512, 1) reduce_scatter_kernel(RSArgs a) {
       src[p] = reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.pt.data[p]) + a.off) + (size_t)rank * a.n;
     T* out = reinterpret_cast<T*>(a.out);
     const bool vec_ok = ((a.n * sizeof(T)) % 16 == 0) && (((uintptr_t)out & 15) == 0);
-    const size_t nvec = vec_ok ? a.n / N : 0;
-    const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
-    const size_t lo = min((size_t)blockIdx.x * per, nvec), hi = min(lo + per, nvec);
-    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-      Vec16 in[W];
+    if (vec_ok) {
+      for (size_t v = lo / N + threadIdx.x; v * N < hi; v += blockDim.x) {
+        if (v * N + N <= hi) {
+          Vec16 in[W];
 #pragma unroll
-      for (int p = 0; p < W; ++p) in[p] = ld_stream(src[p] + v * N);
-      float acc[N], f[N];
-      Pack<T>::unpack(in[0], acc);
+          for (int p = 0; p < W; ++p) in[p] = ld_stream(src[p] + v * N);
+          float acc[N], f[N];
+          Pack<T>::unpack(in[0], acc);
 #pragma unroll
-      for (int p = 1; p < W; ++p) {
-        Pack<T>::unpack(in[p], f);
+          for (int p = 1; p < W; ++p) {
+            Pack<T>::unpack(in[p], f);
 #pragma unroll
-        for (int k = 0; k < N; ++k) acc[k] = red<OP>(acc[k], f[k]);
+            for (int k = 0; k < N; ++k) acc[k] = red<OP>(acc[k], f[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc[k] *= a.scale;
+          st_stream(out + v * N, Pack<T>::pack(acc));
+        } else {  // n is a multiple of 16 bytes but not of the vector width of this CTA's last group: cannot happen (per % N == 0)
+          for (size_t e = v * N; e < hi; ++e) {
+            float acc = float(src[0][e]);
+#pragma unroll
+            for (int p = 1; p < W; ++p) acc = red<OP>(acc, float(src[p][e]));
+            out[e] = T(acc * a.scale);
+          }
+        }
       }
-#pragma unroll
-      for (int k = 0; k < N; ++k) acc[k] *= a.scale;
-      st_stream(out + v * N, Pack<T>::pack(acc));
-    }
-    if (!vec_ok) {  // odd sizes / unaligned slots: scalar path (slots then start at unaligned addresses)
-      for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (size_t)gridDim.x * blockDim.x) {
+    } else {  // odd sizes: slots start at unaligned addresses, scalar path over the same element range
+      for (size_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
         float acc = float(src[0][e]);
 #pragma unroll
         for (int p = 1; p < W; ++p) acc = red<OP>(acc, float(src[p][e]));
