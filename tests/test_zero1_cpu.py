@@ -230,3 +230,53 @@ def test_commit_on_device_vetoes_when_errored_or_too_few_replicas_and_syncs_when
             assert m._step == 1
         finally:
             m.shutdown(wait=False)
+
+
+# ----------------------------------------------------------------------------- liveness-driven abort
+def test_liveness_watch_aborts_the_group_when_a_quorum_member_stops_heartbeating(monkeypatch):
+    """Reference analogue: user-space op timeout -> ncclCommAbort (process_group.py:738-763), which costs the full
+    collective timeout. Here the Manager asks the Lighthouse who is still heart-beating and releases the spinning
+    kernels (pg.abort()) about one heartbeat timeout after a peer went silent."""
+    import threading
+    import time
+
+    from torchft_b200.bench_utils import loopback
+    from torchft_b200.coordination import LighthouseServer
+    from torchft_b200.manager import Manager
+    from torchft_b200.process_group import ProcessGroupDummy
+
+    monkeypatch.setenv("TORCHFT_B200_LIVENESS_ABORT", "1")
+    aborts = []
+
+    class PG(ProcessGroupDummy):
+        def abort(self, *a, **k):
+            aborts.append(time.monotonic())
+
+        def errored(self):
+            return None
+
+    lh = LighthouseServer(bind="[::]:0", min_replicas=1, join_timeout_ms=1000, heartbeat_timeout_ms=600)
+    addr = loopback(lh.address())
+    stores, managers = [], []
+    for name in ("live_0", "live_1"):
+        st = TCPStore("127.0.0.1", 0, is_master=True, wait_for_workers=False)
+        stores.append(st)
+        managers.append(Manager(pg=PG(0, 1), load_state_dict=lambda s: None, state_dict=lambda: {}, min_replica_size=1, rank=0,
+                                world_size=1, store_addr="127.0.0.1", store_port=st.port, lighthouse_addr=addr, replica_id=name,
+                                timeout=timedelta(seconds=5), init_sync=False, checkpoint_transport=MagicMock()))
+    try:
+        ts = [threading.Thread(target=lambda m=m: (m.start_quorum(), m.wait_quorum())) for m in managers]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert len(managers[0]._quorum_members) == 2
+        time.sleep(0.8)
+        assert aborts == []                      # everybody alive: nothing is aborted
+        t0 = time.monotonic()
+        managers[1]._manager.shutdown()          # the peer's heartbeats stop (process death)
+        while not aborts and time.monotonic() - t0 < 5:
+            time.sleep(0.05)
+        assert aborts and aborts[0] - t0 < 2.5   # ~ heartbeat timeout + one poll period, not the 5 s op timeout
+    finally:
+        for m in managers:
+            m.shutdown(wait=False)
+        lh.shutdown()

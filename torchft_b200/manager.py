@@ -176,8 +176,8 @@ class _LivenessWatch(threading.Thread):
         from torchft_b200.coordination import lighthouse_status
 
         while not self._halt.wait(self.period_s):
-            members = self._members()
-            if len(members) < 2:
+            members = self._members()  # the OTHER members of the current quorum
+            if not members:
                 continue
             try:
                 st = lighthouse_status(self._addr, timedelta(seconds=2))
