@@ -255,6 +255,8 @@ def test_liveness_watch_aborts_the_group_when_a_quorum_member_stops_heartbeating
         def errored(self):
             return None
 
+    transport = MagicMock()
+    transport.metadata.return_value = "none"
     lh = LighthouseServer(bind="[::]:0", min_replicas=1, join_timeout_ms=1000, heartbeat_timeout_ms=600)
     addr = loopback(lh.address())
     stores, managers = [], []
@@ -263,7 +265,7 @@ def test_liveness_watch_aborts_the_group_when_a_quorum_member_stops_heartbeating
         stores.append(st)
         managers.append(Manager(pg=PG(0, 1), load_state_dict=lambda s: None, state_dict=lambda: {}, min_replica_size=1, rank=0,
                                 world_size=1, store_addr="127.0.0.1", store_port=st.port, lighthouse_addr=addr, replica_id=name,
-                                timeout=timedelta(seconds=5), init_sync=False, checkpoint_transport=MagicMock()))
+                                timeout=timedelta(seconds=5), init_sync=False, checkpoint_transport=transport))
     try:
         ts = [threading.Thread(target=lambda m=m: (m.start_quorum(), m.wait_quorum())) for m in managers]
         [t.start() for t in ts]
