@@ -178,6 +178,28 @@ def test_q8_allreduce_and_reduce_scatter_within_reference_tolerance(world):
                 assert ((rs[r][:valid].float() - want).abs().mean() / want.abs().mean()).item() <= 0.05  # :207
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_q8_allreduce_large_message_pipeline_with_scratch_segment(world):
+    """With a ``*_q8`` scratch segment the fp8 all-reduce runs as quantise -> handshake -> slice-reduce -> handshake ->
+    gather+dequantise (sync-free kernels of any grid size): same numerics contract, same result on every rank."""
+    n = (3 << 20) + 40
+    comms = _world(world, segs={"buf": 1 << 20, "frag_q8": (n * 516 // 512 + 16 * 516 + 4096) * 3 // 2 + 8192})
+    g = torch.Generator(device=DEV).manual_seed(21)
+    for dtype in (torch.float32, torch.bfloat16):
+        a = [(torch.randn(n, device=DEV, generator=g) * 2).to(dtype) for _ in range(world)]
+        b = [torch.randn(n, device=DEV, generator=g).to(dtype) for _ in range(world)]
+        outs = [torch.empty(n, dtype=dtype, device=DEV) for _ in range(world)]
+        before = [c.launches for c in comms]
+        _run(comms, lambda r, c, s: c.q8_allreduce_(outs[r], a[r], b[r], scale=1.0 / world, contribute=(r != 1 or world == 2), stream=s))
+        _ok(comms)
+        assert [c.launches - x for c, x in zip(comms, before)] == [5] * world  # 3 kernels + 2 handshakes, ONE pass
+        quiet = None if world == 2 else 1
+        ref = sum(x.float() - y.float() for r, (x, y) in enumerate(zip(a, b)) if r != quiet) / world
+        for o in outs:
+            assert ((o.float() - ref).abs().mean() / ref.abs().mean()).item() <= 0.04
+        assert all(torch.equal(outs[0], o) for o in outs)
+
+
 def test_dead_rank_latches_timeout_instead_of_hanging_then_abort_is_immediate():
     import time
 

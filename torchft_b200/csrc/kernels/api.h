@@ -69,6 +69,11 @@ void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const
                          uint64_t flag, int channel, int contribute, int blocks, int barrier_mode,
                          cudaStream_t stream);
 
+size_t q8_slice_buffer_bytes(size_t nelem, int world);
+void q8_slice_reduce_launch(const PeerTable& pt, const int* ok, size_t q_off, size_t r_off, size_t nelem, float post_scale,
+                            int blocks, cudaStream_t stream);
+void q8_gather_dequant_launch(const PeerTable& pt, const int* ok, size_t r_off, size_t nelem, int dtype, void* out, int blocks,
+                              cudaStream_t stream);
 size_t q8_rs_buffer_bytes(size_t slice_elems, int world);
 void q8_reduce_scatter_launch(const PeerTable& pt, StatusBlock* st, size_t off, const void* in, void* out, size_t nelem,
                               size_t slice_elems, int dtype, float post_scale, uint64_t flag, int channel,

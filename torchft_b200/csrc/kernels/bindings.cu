@@ -329,6 +329,15 @@ PYBIND11_MODULE(_K, m) {
       py::arg("out"), py::arg("nelem"), py::arg("dtype"), py::arg("post_scale"), py::arg("flag"),
       py::arg("channel"), py::arg("contribute"), py::arg("blocks"), py::arg("barrier_mode"), py::arg("stream"));
 
+  m.def("q8_slice_buffer_bytes", &q8_slice_buffer_bytes);
+  m.def("q8_slice_reduce", [](const PeerTableH& pt, uintptr_t ok, size_t q_off, size_t r_off, size_t nelem, float post_scale,
+                               int blocks, uintptr_t stream) {
+    q8_slice_reduce_launch(pt.pt, P<const int>(ok), q_off, r_off, nelem, post_scale, blocks, S(stream));
+  });
+  m.def("q8_gather_dequant", [](const PeerTableH& pt, uintptr_t ok, size_t r_off, size_t nelem, int dtype, uintptr_t out,
+                                 int blocks, uintptr_t stream) {
+    q8_gather_dequant_launch(pt.pt, P<const int>(ok), r_off, nelem, dtype, P<void>(out), blocks, S(stream));
+  });
   m.def("q8_rs_buffer_bytes", &q8_rs_buffer_bytes);
   m.def(
       "q8_reduce_scatter",

@@ -348,6 +348,77 @@ __global__ void __launch_bounds__(512, 1) q8_allreduce_kernel(Q8Args a) {
   }
 }
 
+// ------------------------------- large messages: sync-free phases ---------------------------
+// For multi-GB messages (DiLoCo's outer step: the whole model) the fused kernel above is limited by its own structure:
+// per-CTA barriers cap the grid at what is co-resident and one warp per group leaves little memory-level parallelism.
+// With a scratch segment that holds the whole message in wire format the pipeline is three bandwidth-bound launches
+// separated by one-CTA handshakes (zero1.cu):
+//     q8_quantize_kernel (any grid)          a - b -> Q8G in MY scratch
+//     handshake
+//     q8_slice_reduce_kernel (any grid)      my slice of every peer's scratch (P2P loads) -> fp32 sum, scale, requantise -> my R
+//     handshake
+//     q8_gather_dequant_kernel (any grid)    slice s from peer s's R (P2P loads) -> dequantise -> out   (the all-gather IS the read)
+struct Q8Ptrs {
+  const char* p[kMaxRanks];
+};
+
+__global__ void __launch_bounds__(512) q8_slice_reduce_kernel(Q8Ptrs q, int world, int rank, size_t ngroups, size_t slice,
+                                                              float post_scale, char* __restrict__ r_out,
+                                                              const int* __restrict__ ok) {
+  if (ok != nullptr && *ok == 0) return;
+  const size_t poff = q8_payload_off(ngroups), rpoff = q8_payload_off(slice);
+  const int lane = threadIdx.x & 31;
+  const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t l = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); l < slice; l += warps) {
+    const size_t g = (size_t)rank * slice + l;
+    Vec16 qv[kMaxRanks];
+    float sv[kMaxRanks];
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; ++k) {  // all loads first; summation starts at own rank and wraps (order determinism)
+      if (k < world) {
+        const char* src = q.p[(rank + k) % world];
+        qv[k] = ld_stream(src + poff + g * kGroup + lane * 16);
+        sv[k] = __ldcv(reinterpret_cast<const float*>(src) + g);
+      }
+    }
+    float acc[16];
+    dequant16(qv[0], sv[0], acc);
+#pragma unroll
+    for (int k = 1; k < kMaxRanks; ++k) {
+      if (k < world) {
+        float f[16];
+        dequant16(qv[k], sv[k], f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] += f[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] *= post_scale;
+    Vec16 out;
+    const float sc = group_quant(acc, &out);
+    if (lane == 0) reinterpret_cast<float*>(r_out)[l] = sc;
+    st_stream(r_out + rpoff + l * kGroup + lane * 16, out);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) q8_gather_dequant_kernel(Q8Ptrs r, size_t ngroups, size_t slice, T* __restrict__ out,
+                                                                size_t nelem, const int* __restrict__ ok) {
+  if (ok != nullptr && *ok == 0) return;
+  const size_t rpoff = q8_payload_off(slice);
+  const int lane = threadIdx.x & 31;
+  const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t g = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += warps) {
+    const size_t e = g * kGroup + lane * 16;
+    if (e >= nelem) continue;
+    const size_t s = g / slice, l = g - s * slice;
+    const char* src = r.p[s];
+    float f[16];
+    dequant16(ld_stream(src + rpoff + l * kGroup + lane * 16), __ldcv(reinterpret_cast<const float*>(src) + l), f);
+    store16<T>(out, e, nelem, f);
+  }
+}
+
 // ------------------------------- launchers ----------------------------------
 size_t q8_ngroups(size_t nelem, int world) {
   size_t g = (nelem + kGroup - 1) / kGroup;
@@ -505,6 +576,39 @@ void q8_allreduce_launch(const PeerTable& pt, StatusBlock* st, size_t off, const
     case kBF16: q8_ar_w<__nv_bfloat16>(a, blocks, stream); break;
     case kF16: q8_ar_w<__half>(a, blocks, stream); break;
     default: throw std::runtime_error("q8_allreduce: unsupported dtype");
+  }
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+size_t q8_slice_buffer_bytes(size_t nelem, int world) {
+  const size_t slice = q8_ngroups(nelem, world) / (world < 1 ? 1 : world);
+  return (q8_payload_off(slice) + slice * kGroup + 255) & ~size_t(255);
+}
+
+void q8_slice_reduce_launch(const PeerTable& pt, const int* ok, size_t q_off, size_t r_off, size_t nelem, float post_scale,
+                            int blocks, cudaStream_t stream) {
+  const size_t ng = q8_ngroups(nelem, pt.world), slice = ng / pt.world;
+  Q8Ptrs q;
+  for (int p = 0; p < kMaxRanks; ++p) q.p[p] = p < pt.world ? reinterpret_cast<const char*>(pt.data[p]) + q_off : nullptr;
+  if (blocks < 1) blocks = 1;
+  q8_slice_reduce_kernel<<<blocks, 512, 0, stream>>>(q, pt.world, pt.rank, ng, slice, post_scale,
+                                                     reinterpret_cast<char*>(pt.data[pt.rank]) + r_off, ok);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void q8_gather_dequant_launch(const PeerTable& pt, const int* ok, size_t r_off, size_t nelem, int dtype, void* out, int blocks,
+                              cudaStream_t stream) {
+  const size_t ng = q8_ngroups(nelem, pt.world), slice = ng / pt.world;
+  Q8Ptrs r;
+  for (int p = 0; p < kMaxRanks; ++p) r.p[p] = p < pt.world ? reinterpret_cast<const char*>(pt.data[p]) + r_off : nullptr;
+  if (blocks < 1) blocks = 1;
+  switch (dtype) {
+    case kF32: q8_gather_dequant_kernel<float><<<blocks, 512, 0, stream>>>(r, ng, slice, (float*)out, nelem, ok); break;
+    case kBF16:
+      q8_gather_dequant_kernel<__nv_bfloat16><<<blocks, 512, 0, stream>>>(r, ng, slice, (__nv_bfloat16*)out, nelem, ok);
+      break;
+    case kF16: q8_gather_dequant_kernel<__half><<<blocks, 512, 0, stream>>>(r, ng, slice, (__half*)out, nelem, ok); break;
+    default: throw std::runtime_error("q8_gather_dequant: unsupported dtype");
   }
   TFT_CUDA_CHECK(cudaGetLastError());
 }

@@ -267,7 +267,9 @@ class _StreamingDiLoCoFragment:
         try:
             buf = alloc(f"diloco_f{self._fragment_id}_flat", span * es)
             if self.should_quantize:  # scratch for the Q8G wire format: the whole fragment in one launch
-                alloc(f"diloco_f{self._fragment_id}_q8", span * 516 // 512 + 16 * 516 + 4096)
+                # whole fragment in wire format (fp32 scale + 512 e4m3 bytes per group, padded to a multiple of 8 groups)
+                # + this rank's reduced slice (at most half of it again, at world 2)
+                alloc(f"diloco_f{self._fragment_id}_q8", (span * 516 // 512 + 16 * 516 + 4096) * 3 // 2 + 8192)
         except Exception:  # noqa: BLE001 - group already configured etc.
             logger.exception("flat DiLoCo path unavailable (symmetric memory); using the generic path")
             return False

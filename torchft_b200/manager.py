@@ -292,6 +292,7 @@ class Manager:
         self._recovery_event: Optional[torch.cuda.Event] = None
         self._commit_gate: Optional[torch.Tensor] = None
         self._liveness: Optional[_LivenessWatch] = None
+        self._reported_dead: set = set()
 
         if self._group_rank == 0:
             if port is None:
@@ -667,7 +668,10 @@ class Manager:
         return [rid for rid in self._quorum_members if rid != self._full_replica_id]
 
     def _peer_died(self, replica_id: str) -> None:
-        if self._pg.errored() is None:
+        # NOT pg.errored(): on the native group that synchronises the comm stream -- i.e. it would wait for the very kernel
+        # that is spinning on the dead peer (measured: the abort then only fired after the full collective timeout)
+        if replica_id not in self._reported_dead:
+            self._reported_dead.add(replica_id)
             self._logger.warn(f"lighthouse lost the heartbeat of {replica_id}: aborting in-flight collectives")
             self.errors_logger.info("", extra={**self._log_tags(), "quorum_id": self._quorum_id, "step": self._ledger.step,
                                                "error": f"peer {replica_id} stopped heart-beating"})

@@ -485,17 +485,26 @@ class SymmetricComm:
                     out.copy_(res)
                 return
             es = a.element_size()
-            # a dedicated scratch segment ("<name>_q8", allocated by the caller before the first quorum) that holds the
-            # whole message in wire format: ONE launch instead of one per 256 MB staging chunk
-            need = self._K.q8_buffer_bytes(a.numel(), self._world)
+            # a dedicated scratch segment ("<name>_q8", allocated by the caller before the first quorum) that holds the whole
+            # message in wire format (+ this rank's reduced slice): three bandwidth-bound launches of any grid size
+            # separated by one-CTA handshakes instead of one barrier-laden launch per 256 MB staging chunk
+            n = a.numel()
+            q_bytes = (self._K.q8_buffer_bytes(n, self._world) + 255) // 256 * 256
+            need = q_bytes + self._K.q8_slice_buffer_bytes(n, self._world)
             for name, seg in self._segments.items():
                 if name.endswith("_q8") and seg.nbytes >= need:
-                    n = a.numel()
-                    blocks = max(4, min(self._q8_max_blocks, (n // 512) // 32 + 1))
-                    K.q8_allreduce(self._tables[name], self._status, 0, a.data_ptr(), b.data_ptr() if b is not None else 0,
-                                   out.data_ptr(), n, dt, scale, self._next_flag(), _CH_Q8, contribute, blocks,
-                                   self._barrier_mode, sp)
-                    self.launches += 1
+                    table = self._tables[name]
+                    ngroups = self._K.q8_ngroups(n, self._world)
+                    big = max(1, min(148 * 16, ngroups // 16 + 1))
+                    if contribute:
+                        K.q8_quantize_raw(a.data_ptr(), b.data_ptr() if b is not None else 0, n, ngroups, dt, seg.ptr, sp)
+                    else:
+                        K.memset_async(seg.ptr, 0, q_bytes, sp)  # zero scales: this replica adds nothing
+                    self._handshake(2, True, _CH_Q8, sp)
+                    K.q8_slice_reduce(table, self._z1_ok(2), 0, q_bytes, n, scale, max(1, min(148 * 8, ngroups // self._world // 16 + 1)), sp)
+                    self._handshake(2, True, _CH_Q8, sp)
+                    K.q8_gather_dequant(table, self._z1_ok(2), q_bytes, n, dt, out.data_ptr(), big, sp)
+                    self.launches += 3
                     return
             # elements per launch such that the Q8G buffer fits in staging
             per = (self._staging_usable * 512 // 516) // (512 * self._world) * (512 * self._world) - 512 * self._world
