@@ -1,4 +1,5 @@
-"""Debug aid: HSDPTrainer on ONE GPU (1 group x 1 shard): exercises FSDP2's hooks against the fused model ops."""
+"""Debug aid: HSDPTrainer on ONE GPU (1 group x 1 shard): exercises FSDP2's hooks against the fused model ops and
+reports where non-finite values first appear (gradients per parameter, then parameters after the optimizer step)."""
 import os
 import sys
 from datetime import timedelta
@@ -17,16 +18,32 @@ from torchft_b200.bench_utils import local_lighthouse, loopback  # noqa: E402
 from torchft_b200.parallel.hsdp import HSDPTrainer  # noqa: E402
 
 model = sys.argv[1] if len(sys.argv) > 1 else "llama3_debug"
+backend = sys.argv[2] if len(sys.argv) > 2 else "b200"
 lh = local_lighthouse()
-tr = HSDPTrainer(model, loopback(lh.address()), shards=1, backend=sys.argv[2] if len(sys.argv) > 2 else "b200", timeout=timedelta(seconds=30))
+tr = HSDPTrainer(model, loopback(lh.address()), shards=1, backend=backend, timeout=timedelta(seconds=30))
 cfg = tr.cfg
 S = min(cfg.max_seq_len, 512)
 tok = torch.randint(0, cfg.vocab_size, (2, S), device="cuda")
 tgt = torch.randint(0, cfg.vocab_size, (2, S), device="cuda")
+
+
+def local(t):
+    return t.to_local() if hasattr(t, "to_local") else t
+
+
 for i in range(3):
-    loss = tr.step_device(tok, tgt)
+    tr.optim.zero_grad(set_to_none=True)
+    loss = tr.model(tok, tgt)
+    loss.backward()
     torch.cuda.synchronize()
-    print("step", i, float(loss), "committed", tr.manager.current_step(), flush=True)
+    bad = [(n, str(local(p.grad).dtype)) for n, p in tr.model.named_parameters() if p.grad is not None and not torch.isfinite(local(p.grad)).all()]
+    none = [n for n, p in tr.model.named_parameters() if p.grad is None]
+    gmax = max(float(local(p.grad).abs().max()) for p in tr.model.parameters() if p.grad is not None)
+    print(f"step {i} loss {float(loss.detach()):.4f} non-finite grads: {bad[:8]} none: {none[:4]} gmax {gmax:.3e}", flush=True)
+    tr.optim.step()
+    torch.cuda.synchronize()
+    badp = [n for n, p in tr.model.named_parameters() if not torch.isfinite(local(p.data)).all()]
+    print(f"   committed {tr.manager.current_step()} non-finite params after step: {badp[:8]}", flush=True)
 tr.shutdown()
 lh.shutdown()
 dist.destroy_process_group()
