@@ -31,6 +31,7 @@ def local(t):
     return t.to_local() if hasattr(t, "to_local") else t
 
 
+losses = []
 for i in range(3):
     tr.optim.zero_grad(set_to_none=True)
     loss = tr.model(tok, tgt)
@@ -44,6 +45,9 @@ for i in range(3):
     torch.cuda.synchronize()
     badp = [n for n, p in tr.model.named_parameters() if not torch.isfinite(local(p.data)).all()]
     print(f"   committed {tr.manager.current_step()} non-finite params after step: {badp[:8]}", flush=True)
+    losses.append(float(loss.detach()))
+    assert not bad and not badp, (bad, badp)
+assert losses[-1] < losses[0], losses  # same batch every step: the loss must go down
 tr.shutdown()
 lh.shutdown()
 dist.destroy_process_group()

@@ -8,14 +8,14 @@ cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/ncu gpurun_out/ncu_csv
 NCU="ncu --set full --clock-control none --import-source on"
 # FT-ZeRO-1 big kernels at W=8 (rank 0's launches: reduce over a 256 MB unit, update of its 2 held slices)
-$NCU -k regex:'zero1_(reduce|update)_kernel' -s 6 -c 2 -o gpurun_out/ncu/zero1_w8 -f \
+$NCU -k regex:'zero1_(reduce|update)_kernel' -s 1 -c 2 -o gpurun_out/ncu/zero1_w8 -f \
   python bench/zero1_bench.py --virtual 8 --mb 256 --iters 1 --warmup 1 > gpurun_out/ncu/zero1_w8.log 2>&1
 # world-1 update (= the flagship's AdamW at N=1)
-$NCU -k regex:'zero1_update_kernel' -s 3 -c 1 -o gpurun_out/ncu/zero1_update_w1 -f \
+$NCU -k regex:'zero1_update_kernel' -s 11 -c 1 -o gpurun_out/ncu/zero1_update_w1 -f \
   python bench/kernel_micro.py --only zero1_update --iters 1 > gpurun_out/ncu/micro_a.log 2>&1
 $NCU -k regex:'diloco_outer_kernel' -s 3 -c 1 -o gpurun_out/ncu/diloco_outer -f \
   python bench/kernel_micro.py --only diloco_outer --iters 1 > gpurun_out/ncu/micro_b.log 2>&1
-$NCU -k regex:'heal_copy_kernel' -s 3 -c 1 -o gpurun_out/ncu/heal_copy_lsu -f \
+$NCU -k regex:'heal_copy_kernel' -s 11 -c 1 -o gpurun_out/ncu/heal_copy_lsu -f \
   python bench/kernel_micro.py --only heal_copy --iters 1 > gpurun_out/ncu/micro_c.log 2>&1
 $NCU -k regex:'heal_copy_bulk_kernel' -s 3 -c 1 -o gpurun_out/ncu/heal_copy_bulk -f \
   python bench/kernel_micro.py --only heal_copy --iters 1 > gpurun_out/ncu/micro_d.log 2>&1

@@ -356,6 +356,7 @@ PYBIND11_MODULE(_K, m) {
     rmsnorm_fwd_launch(P<void>(x), P<void>(w), P<void>(y), P<float>(rstd), rows, H, eps, S(s));
   });
   m.def("rmsnorm_bwd_grid", &rmsnorm_bwd_grid);
+  m.def("rmsnorm_tune", &rmsnorm_tune, "CTA size (128/256/512), prefetch next row, CTAs/SM at 128 threads");
   m.def("rmsnorm_bwd", [](uintptr_t dy, uintptr_t x, uintptr_t w, uintptr_t rstd, uintptr_t dx,
                           uintptr_t dw_partial, uintptr_t dw, bool accumulate, int rows, int H,
                           uintptr_t s, uintptr_t dres) {
@@ -373,6 +374,12 @@ PYBIND11_MODULE(_K, m) {
                    size_t in_stride, size_t out_stride, float sign, uintptr_t s) {
     rope_launch(P<void>(in), P<void>(out), P<void>(cs), T, S_, heads, D, in_stride, out_stride, sign, S(s));
   });
+  m.def("rope_qkv", [](uintptr_t packed, size_t row, uintptr_t q, uintptr_t k, uintptr_t v, std::vector<int64_t> strides,
+                       uintptr_t cs, size_t T, int S_, int D, int Hq, int Hkv, int dir, uintptr_t s) {
+    if (strides.size() != 9) throw std::runtime_error("rope_qkv: strides = (batch, position, head) x (q, k, v)");
+    rope_qkv_launch(P<void>(packed), row, P<void>(q), P<void>(k), P<void>(v), strides.data(), P<void>(cs), T, S_, D, Hq,
+                    Hkv, dir, S(s));
+  }, "RoPE + q/k/v split of a packed projection (dir 0) or its backward (dir 1), one launch");
   m.def("xent", [](uintptr_t logits, uintptr_t target, uintptr_t loss, size_t rows, int V,
                    size_t row_stride, float grad_scale, long long ignore_index, uintptr_t s) {
     xent_launch(P<void>(logits), P<void>(target), P<float>(loss), rows, V, row_stride, grad_scale,

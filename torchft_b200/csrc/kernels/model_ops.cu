@@ -7,7 +7,9 @@
 // elementwise/normalisation/activation step is one pass over HBM with 16 B
 // accesses; GEMMs stay on cuBLAS and attention on the SDPA library kernel.
 // All activations are bf16, all reductions fp32.
+#include <algorithm>
 #include <stdexcept>
+#include <type_traits>
 #include <string>
 
 #include "api.h"
@@ -19,44 +21,84 @@ using bf16 = __nv_bfloat16;
 using P8 = Pack<bf16>;
 
 // ------------------------------- RMSNorm ------------------------------------
-// One CTA per row, row cached in registers (H <= 8 * 4 * blockDim).
+// A CTA of TPB threads walks rows blockIdx.x, +gridDim.x, ...; a thread owns NV 16-byte vectors of the row (H <= 8*NV*TPB),
+// kept PACKED in registers. The row-wide sum costs ONE __syncthreads (warp partials in a double-buffered smem line, every
+// thread adds the <= 16 partials itself), and with PF the next row's loads are issued before the current row's reduction so
+// a CTA always has a full row of 16 B loads in flight. Small CTAs (128 threads x 4 vectors) with 4 per SM keep ~64 KB per
+// SM in flight, which is what HBM3e needs (B200_PROFILING.md: ~40 KB/SM by Little's law); one 512-thread CTA with one
+// vector per thread and three barriers per row (round 1) reached 62 % (fwd) / 43 % (bwd) of the measured copy bandwidth.
 constexpr int kRmsMaxVec = 4;
+static int g_rms_tpb = 128, g_rms_pf = 1, g_rms_cps = 4;
 
-template <int NV>
-__global__ void __launch_bounds__(512) rmsnorm_fwd_kernel(const bf16* __restrict__ x,
-                                                          const bf16* __restrict__ w,
-                                                          bf16* __restrict__ y,
-                                                          float* __restrict__ rstd, int rows, int H,
-                                                          float eps) {
-  __shared__ float red[32];
+template <int TPB>
+__device__ __forceinline__ float row_sum(float v, float (*red)[TPB / 32], int& parity) {
+  v = warp_sum(v);
+  constexpr int NW = TPB / 32;
+  if ((threadIdx.x & 31) == 0) red[parity][threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) r += red[parity][i];
+  parity ^= 1;  // the next row writes the other line: nobody can be two barriers ahead of a reader
+  return r;
+}
+
+template <int NV, int TPB, bool PF>
+__global__ void __launch_bounds__(TPB) rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                          bf16* __restrict__ y, float* __restrict__ rstd, int rows,
+                                                          int H, float eps) {
+  __shared__ float red[2][TPB / 32];
   const int nvec = H / 8;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const bf16* xr = x + (size_t)row * H;
-    float f[NV][8];
+  int parity = 0;
+  Vec16 wv[NV], xv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = threadIdx.x + i * TPB;
+    if (v < nvec) wv[i] = *reinterpret_cast<const Vec16*>(w + v * 8);
+  }
+  auto load_row = [&](int row, Vec16* dst) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = threadIdx.x + i * TPB;
+      if (v < nvec) dst[i] = ld_stream(x + (size_t)row * H + v * 8);
+    }
+  };
+  int row = blockIdx.x;
+  if (row < rows) load_row(row, xv);
+  for (; row < rows; row += gridDim.x) {
+    const int next = row + gridDim.x;
+    Vec16 nx[NV];
+    if (PF && next < rows) load_row(next, nx);
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int v = threadIdx.x + i * blockDim.x;
-      if (v < nvec) {
-        P8::unpack(ld_stream(xr + v * 8), f[i]);
+      if (threadIdx.x + i * TPB < nvec) {
+        float f[8];
+        P8::unpack(xv[i], f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) ss += f[i][k] * f[i][k];
+        for (int k = 0; k < 8; ++k) ss += f[k] * f[k];
       }
     }
-    ss = block_sum(ss, red);
+    ss = row_sum<TPB>(ss, red, parity);
     const float r = rsqrtf(ss / H + eps);
     if (threadIdx.x == 0) rstd[row] = r;
-    bf16* yr = y + (size_t)row * H;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int v = threadIdx.x + i * blockDim.x;
+      const int v = threadIdx.x + i * TPB;
       if (v < nvec) {
-        float wf[8], o[8];
-        P8::unpack(*reinterpret_cast<const Vec16*>(w + v * 8), wf);
+        float f[8], wf[8], o[8];
+        P8::unpack(xv[i], f);
+        P8::unpack(wv[i], wf);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = f[i][k] * r * wf[k];
-        st_stream(yr + v * 8, P8::pack(o));
+        for (int k = 0; k < 8; ++k) o[k] = f[k] * r * wf[k];
+        st_stream(y + (size_t)row * H + v * 8, P8::pack(o));
       }
+    }
+    if (PF) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xv[i] = nx[i];
+    } else if (next < rows) {
+      load_row(next, xv);
     }
   }
 }
@@ -64,63 +106,101 @@ __global__ void __launch_bounds__(512) rmsnorm_fwd_kernel(const bf16* __restrict
 // dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) (+ dres); dw_partial[block] += dy * xhat
 // dres (optional) is the gradient arriving over the residual connection that bypasses the norm:
 // adding it here saves the separate elementwise accumulation pass autograd would run.
-template <int NV>
-__global__ void __launch_bounds__(512) rmsnorm_bwd_kernel(
+template <int NV, int TPB, bool PF>
+__global__ void __launch_bounds__(TPB) rmsnorm_bwd_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
     const float* __restrict__ rstd, bf16* __restrict__ dx, float* __restrict__ dw_partial,
     const bf16* __restrict__ dres, int rows, int H) {
-  __shared__ float red[32];
+  __shared__ float red[2][TPB / 32];
   const int nvec = H / 8;
+  int parity = 0;
   float dw[NV][8];
-  float wf[NV][8];
+  Vec16 wv[NV], xv[NV], gv[NV], rv[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int v = threadIdx.x + i * blockDim.x;
+    const int v = threadIdx.x + i * TPB;
 #pragma unroll
     for (int k = 0; k < 8; ++k) dw[i][k] = 0.f;
-    if (v < nvec) P8::unpack(*reinterpret_cast<const Vec16*>(w + v * 8), wf[i]);
+    if (v < nvec) wv[i] = *reinterpret_cast<const Vec16*>(w + v * 8);
   }
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const float r = rstd[row];
-    float xh[NV][8], g[NV][8];
+  auto load_row = [&](int row, Vec16* xd, Vec16* gd, Vec16* rd) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = threadIdx.x + i * TPB;
+      if (v < nvec) {
+        const size_t o = (size_t)row * H + v * 8;
+        xd[i] = ld_stream(x + o);
+        gd[i] = ld_stream(dy + o);
+        if (dres != nullptr) rd[i] = ld_stream(dres + o);
+      }
+    }
+  };
+  int row = blockIdx.x;
+  float r = 0.f;
+  if (row < rows) {
+    load_row(row, xv, gv, rv);
+    r = rstd[row];
+  }
+  for (; row < rows; row += gridDim.x) {
+    const int next = row + gridDim.x;
+    Vec16 nx[NV], ng[NV], nr[NV];
+    float rn = 0.f;
+    if (PF && next < rows) {
+      load_row(next, nx, ng, nr);
+      rn = rstd[next];
+    }
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int v = threadIdx.x + i * blockDim.x;
-      if (v < nvec) {
-        float xf[8], dyf[8];
-        P8::unpack(ld_stream(x + (size_t)row * H + v * 8), xf);
-        P8::unpack(ld_stream(dy + (size_t)row * H + v * 8), dyf);
+      if (threadIdx.x + i * TPB < nvec) {
+        float xf[8], dyf[8], wf[8];
+        P8::unpack(xv[i], xf);
+        P8::unpack(gv[i], dyf);
+        P8::unpack(wv[i], wf);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          xh[i][k] = xf[k] * r;
-          g[i][k] = dyf[k] * wf[i][k];
-          dot += g[i][k] * xh[i][k];
-          dw[i][k] += dyf[k] * xh[i][k];
+          const float xh = xf[k] * r;
+          dot += dyf[k] * wf[k] * xh;
+          dw[i][k] += dyf[k] * xh;
         }
       }
     }
-    dot = block_sum(dot, red) / H;
+    dot = row_sum<TPB>(dot, red, parity) / H;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int v = threadIdx.x + i * blockDim.x;
+      const int v = threadIdx.x + i * TPB;
       if (v < nvec) {
-        float o[8];
+        float xf[8], dyf[8], wf[8], o[8];
+        P8::unpack(xv[i], xf);
+        P8::unpack(gv[i], dyf);
+        P8::unpack(wv[i], wf);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = r * (g[i][k] - xh[i][k] * dot);
+        for (int k = 0; k < 8; ++k) o[k] = r * (dyf[k] * wf[k] - xf[k] * r * dot);
         if (dres != nullptr) {
           float rf[8];
-          P8::unpack(ld_stream(dres + (size_t)row * H + v * 8), rf);
+          P8::unpack(rv[i], rf);
 #pragma unroll
           for (int k = 0; k < 8; ++k) o[k] += rf[k];
         }
         st_stream(dx + (size_t)row * H + v * 8, P8::pack(o));
       }
     }
+    if (PF) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xv[i] = nx[i];
+        gv[i] = ng[i];
+        rv[i] = nr[i];
+      }
+      r = rn;
+    } else if (next < rows) {
+      load_row(next, xv, gv, rv);
+      r = rstd[next];
+    }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int v = threadIdx.x + i * blockDim.x;
+    const int v = threadIdx.x + i * TPB;
     if (v < nvec) {
       float* o = dw_partial + (size_t)blockIdx.x * H + v * 8;
       *reinterpret_cast<float4*>(o) = make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]);
@@ -129,15 +209,33 @@ __global__ void __launch_bounds__(512) rmsnorm_bwd_kernel(
   }
 }
 
-// dw[h] (+)= sum_b partial[b][h]
-__global__ void colsum_kernel(const float* __restrict__ partial, int nb, int H,
-                              bf16* __restrict__ dw, int accumulate) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
-  float s = 0.f;
-  for (int b = 0; b < nb; ++b) s += partial[(size_t)b * H + h];
-  if (accumulate) s += __bfloat162float(dw[h]);
-  dw[h] = __float2bfloat16(s);
+// dw[h] (+)= sum_b partial[b][h]: a CTA owns 32 columns, its 8 warps stride over the partial rows (each warp load is one
+// 128 B line), then the 8 per-warp sums meet in shared memory.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ partial, int nb, int H,
+                                                     bf16* __restrict__ dw, int accumulate) {
+  __shared__ float acc[8][33];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int h = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (h < H) {
+    int b = wrp;
+    for (; b + 24 < nb; b += 32) {
+      s0 += partial[(size_t)b * H + h];
+      s1 += partial[(size_t)(b + 8) * H + h];
+      s2 += partial[(size_t)(b + 16) * H + h];
+      s3 += partial[(size_t)(b + 24) * H + h];
+    }
+    for (; b < nb; b += 8) s0 += partial[(size_t)b * H + h];
+  }
+  acc[wrp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (wrp == 0 && h < H) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i][lane];
+    if (accumulate) s += __bfloat162float(dw[h]);
+    dw[h] = __float2bfloat16(s);
+  }
 }
 
 // ------------------------------- SwiGLU -------------------------------------
@@ -187,31 +285,107 @@ __global__ void __launch_bounds__(512) swiglu_bwd_kernel(const bf16* __restrict_
 // (cos, sin) pairs: cs[pos][i] = float2. sign = +1 forward, -1 backward.
 // in/out row strides in elements so q/k can be read straight out of the packed
 // qkv projection and written contiguous.
-__global__ void __launch_bounds__(256) rope_kernel(const bf16* __restrict__ in,
-                                                   bf16* __restrict__ out,
-                                                   const float2* __restrict__ cs, size_t T, int S,
-                                                   int heads, int D, size_t in_stride,
-                                                   size_t out_stride, float sign) {
-  const int vec_per_head = D / 8;
-  const size_t total = T * heads * vec_per_head;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int vh = i % vec_per_head;
-    const size_t th = i / vec_per_head;
-    const int h = th % heads;
-    const size_t t = th / heads;
-    const int pos = t % S;
-    float f[8], o[8];
-    P8::unpack(ld_stream(in + t * in_stride + (size_t)h * D + vh * 8), f);
-    const float2* c = cs + (size_t)pos * (D / 2) + vh * 4;
+// A thread keeps its vector-in-head index for the whole kernel and walks (token, head) "slots" two at a time (both 16 B
+// loads issued before either is used); all index math is 32-bit (round 1 did three 64-bit divisions per vector and had one
+// load in flight per thread: 60 % of the measured copy bandwidth).
+__global__ void __launch_bounds__(256) rope_kernel(const bf16* __restrict__ in, bf16* __restrict__ out,
+                                                   const float2* __restrict__ cs, unsigned nslots, unsigned S,
+                                                   unsigned heads, unsigned D, size_t in_stride, size_t out_stride,
+                                                   float sign) {
+  const unsigned vph = D / 8;
+  const unsigned vh = threadIdx.x % vph, s0 = threadIdx.x / vph, per = blockDim.x / vph;
+  for (unsigned base = blockIdx.x * 2 * per; base < nslots; base += gridDim.x * 2 * per) {
+    Vec16 v[2];
+    unsigned t[2], h[2];
+    bool ok[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 v = c[k];
-      const float sn = v.y * sign;
-      o[2 * k] = f[2 * k] * v.x - f[2 * k + 1] * sn;
-      o[2 * k + 1] = f[2 * k] * sn + f[2 * k + 1] * v.x;
+    for (int j = 0; j < 2; ++j) {
+      const unsigned g = base + s0 + j * per;
+      ok[j] = g < nslots;
+      t[j] = g / heads;
+      h[j] = g - t[j] * heads;
+      if (ok[j]) v[j] = ld_stream(in + (size_t)t[j] * in_stride + h[j] * D + vh * 8);
     }
-    st_stream(out + t * out_stride + (size_t)h * D + vh * 8, P8::pack(o));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (!ok[j]) continue;
+      const unsigned pos = t[j] % S;
+      const float4* c = reinterpret_cast<const float4*>(cs + (size_t)pos * (D / 2) + vh * 4);
+      const float4 c0 = c[0], c1 = c[1];
+      const float cx[4] = {c0.x, c0.z, c1.x, c1.z}, sy[4] = {c0.y, c0.w, c1.y, c1.w};
+      float f[8], o[8];
+      P8::unpack(v[j], f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float sn = sy[k] * sign;
+        o[2 * k] = f[2 * k] * cx[k] - f[2 * k + 1] * sn;
+        o[2 * k + 1] = f[2 * k] * sn + f[2 * k + 1] * cx[k];
+      }
+      st_stream(out + (size_t)t[j] * out_stride + h[j] * D + vh * 8, P8::pack(o));
+    }
+  }
+}
+
+// RoPE + q/k/v split (dir 0: packed qkv projection -> rotated q, rotated k, v) and its backward (dir 1: dq, dk, dv in ANY
+// [B, S, H, D] stride order -> inverse-rotated packed d_qkv) as ONE launch: every (token, head) slot of the packed row is
+// read once and written once; the v heads are a plain copy. Replaces two rope launches plus the library's strided copy of
+// v in forward, and two rope launches plus three .contiguous()/copy_ kernels in backward.
+struct RopeQKVArgs {
+  bf16* packed;
+  size_t row;  // elements per packed row = (Hq + 2 Hkv) * D
+  bf16* sep[3];
+  size_t sb[3], ss[3], sh[3];  // element strides of q / k / v: batch, position, head
+  unsigned nh[3];
+  const float2* cs;
+  unsigned T, S, D;
+  int dir;
+};
+
+__global__ void __launch_bounds__(256) rope_qkv_kernel(const RopeQKVArgs a) {
+  const unsigned vph = a.D / 8;
+  const unsigned vh = threadIdx.x % vph, s0 = threadIdx.x / vph, per = blockDim.x / vph;
+  const unsigned heads = a.nh[0] + a.nh[1] + a.nh[2];
+  const unsigned nslots = a.T * heads;
+  const float sign = a.dir == 0 ? 1.f : -1.f;
+  for (unsigned base = blockIdx.x * 2 * per; base < nslots; base += gridDim.x * 2 * per) {
+    Vec16 v[2];
+    bf16* dst[2];
+    unsigned pos[2];
+    bool ok[2], rot[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const unsigned g = base + s0 + j * per;
+      ok[j] = g < nslots;
+      const unsigned t = g / heads, hh = g - t * heads;
+      const unsigned b = t / a.S;
+      pos[j] = t - b * a.S;
+      const int w = hh < a.nh[0] ? 0 : (hh < a.nh[0] + a.nh[1] ? 1 : 2);
+      const unsigned h = hh - (w == 0 ? 0 : (w == 1 ? a.nh[0] : a.nh[0] + a.nh[1]));
+      rot[j] = w < 2;
+      bf16* pk = a.packed + (size_t)t * a.row + (size_t)hh * a.D + vh * 8;
+      bf16* sp = a.sep[w] + b * a.sb[w] + pos[j] * a.ss[w] + h * a.sh[w] + vh * 8;
+      dst[j] = a.dir == 0 ? sp : pk;
+      if (ok[j]) v[j] = ld_stream(a.dir == 0 ? pk : sp);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (!ok[j]) continue;
+      if (rot[j]) {
+        const float4* c = reinterpret_cast<const float4*>(a.cs + (size_t)pos[j] * (a.D / 2) + vh * 4);
+        const float4 c0 = c[0], c1 = c[1];
+        const float cx[4] = {c0.x, c0.z, c1.x, c1.z}, sy[4] = {c0.y, c0.w, c1.y, c1.w};
+        float f[8], o[8];
+        P8::unpack(v[j], f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float sn = sy[k] * sign;
+          o[2 * k] = f[2 * k] * cx[k] - f[2 * k + 1] * sn;
+          o[2 * k + 1] = f[2 * k] * sn + f[2 * k + 1] * cx[k];
+        }
+        v[j] = P8::pack(o);
+      }
+      st_stream(dst[j], v[j]);
+    }
   }
 }
 
@@ -619,38 +793,69 @@ static int grid_for(size_t work_items, int threads, int cap = 148 * 8) {
   return (int)g;
 }
 
+// (TPB, NV) for a row of nvec 16 B vectors: the tuned CTA size if NV <= 4 covers the row, else the next larger CTA.
+static void rms_shape(int nvec, int& tpb, int& nv) {
+  for (tpb = g_rms_tpb; tpb <= 512; tpb *= 2) {
+    const int need = (nvec + tpb - 1) / tpb;
+    nv = need <= 1 ? 1 : need <= 2 ? 2 : 4;
+    if (need <= kRmsMaxVec) return;
+  }
+  tpb = 512;
+  nv = kRmsMaxVec;
+}
+static int rms_grid(int rows, int tpb) {
+  const int cap = 148 * std::max(1, g_rms_cps * 128 / tpb);
+  return rows < cap ? rows : cap;
+}
+
+void rmsnorm_tune(int tpb, int prefetch, int ctas_per_sm_at_128) {
+  if (tpb != 128 && tpb != 256 && tpb != 512) throw std::runtime_error("rmsnorm_tune: tpb must be 128, 256 or 512");
+  g_rms_tpb = tpb;
+  g_rms_pf = prefetch ? 1 : 0;
+  g_rms_cps = std::max(1, ctas_per_sm_at_128);
+}
+
+#define RMS_DISPATCH(KERNEL, ...)                                                                          \
+  do {                                                                                                     \
+    auto go = [&](auto nvc, auto tpbc, auto pfc) {                                                         \
+      KERNEL<decltype(nvc)::value, decltype(tpbc)::value, decltype(pfc)::value><<<grid, tpb, 0, s>>>(__VA_ARGS__); \
+    };                                                                                                     \
+    auto by_pf = [&](auto nvc, auto tpbc) {                                                                \
+      if (g_rms_pf && !(nv == 4 && tpb == 512)) go(nvc, tpbc, std::true_type{}); else go(nvc, tpbc, std::false_type{}); \
+    };                                                                                                     \
+    auto by_tpb = [&](auto nvc) {                                                                          \
+      if (tpb == 128) by_pf(nvc, std::integral_constant<int, 128>{});                                      \
+      else if (tpb == 256) by_pf(nvc, std::integral_constant<int, 256>{});                                 \
+      else by_pf(nvc, std::integral_constant<int, 512>{});                                                 \
+    };                                                                                                     \
+    if (nv == 1) by_tpb(std::integral_constant<int, 1>{});                                                 \
+    else if (nv == 2) by_tpb(std::integral_constant<int, 2>{});                                            \
+    else by_tpb(std::integral_constant<int, 4>{});                                                         \
+  } while (0)
+
 void rmsnorm_fwd_launch(const void* x, const void* w, void* y, float* rstd, int rows, int H,
                         float eps, cudaStream_t s) {
   if (H % 8 || H > 8 * kRmsMaxVec * 512) throw std::runtime_error("rmsnorm: H must be %8 and <= 16384");
-  const int grid = rows < 148 * 8 ? rows : 148 * 8;
-  const int nv = (H / 8 + 511) / 512;
-  if (nv <= 1)
-    rmsnorm_fwd_kernel<1><<<grid, 512, 0, s>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
-  else if (nv <= 2)
-    rmsnorm_fwd_kernel<2><<<grid, 512, 0, s>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
-  else
-    rmsnorm_fwd_kernel<4><<<grid, 512, 0, s>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
+  int tpb, nv;
+  rms_shape(H / 8, tpb, nv);
+  const int grid = rms_grid(rows, tpb);
+  RMS_DISPATCH(rmsnorm_fwd_kernel, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 
-int rmsnorm_bwd_grid(int rows) { return rows < 296 ? rows : 296; }
+// rows of the fp32 partial-dw buffer the caller must provide (an upper bound on the grid for any H)
+int rmsnorm_bwd_grid(int rows) { return rms_grid(rows, 128); }
 
 void rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                         float* dw_partial, void* dw, int accumulate, int rows, int H,
                         cudaStream_t s, const void* dres) {
   if (H % 8 || H > 8 * kRmsMaxVec * 512) throw std::runtime_error("rmsnorm: H must be %8 and <= 16384");
-  const int grid = rmsnorm_bwd_grid(rows);
-  const int nv = (H / 8 + 511) / 512;
-  if (nv <= 1)
-    rmsnorm_bwd_kernel<1><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
-                                               (bf16*)dx, dw_partial, (const bf16*)dres, rows, H);
-  else if (nv <= 2)
-    rmsnorm_bwd_kernel<2><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
-                                               (bf16*)dx, dw_partial, (const bf16*)dres, rows, H);
-  else
-    rmsnorm_bwd_kernel<4><<<grid, 512, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
-                                               (bf16*)dx, dw_partial, (const bf16*)dres, rows, H);
-  colsum_kernel<<<(H + 255) / 256, 256, 0, s>>>(dw_partial, grid, H, (bf16*)dw, accumulate);
+  int tpb, nv;
+  rms_shape(H / 8, tpb, nv);
+  const int grid = rms_grid(rows, tpb);
+  RMS_DISPATCH(rmsnorm_bwd_kernel, (const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (bf16*)dx, dw_partial,
+               (const bf16*)dres, rows, H);
+  colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(dw_partial, grid, H, (bf16*)dw, accumulate);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -668,9 +873,49 @@ void swiglu_bwd_launch(const void* dy, const void* gu, void* dgu, size_t T, int 
 
 void rope_launch(const void* in, void* out, const void* cs, size_t T, int S, int heads, int D,
                  size_t in_stride, size_t out_stride, float sign, cudaStream_t s) {
-  if (D % 8) throw std::runtime_error("rope: head_dim must be a multiple of 8");
-  rope_kernel<<<grid_for(T * heads * (D / 8), 256), 256, 0, s>>>(
-      (const bf16*)in, (bf16*)out, (const float2*)cs, T, S, heads, D, in_stride, out_stride, sign);
+  if (D % 8 || D > 2048) throw std::runtime_error("rope: head_dim must be a multiple of 8 and <= 2048");
+  if (T * (size_t)heads >= (1ull << 31)) throw std::runtime_error("rope: tokens * heads must be < 2^31");
+  if (T == 0) return;
+  const unsigned vph = D / 8, per = 256 / vph, threads = per * vph;  // whole (token, head) slots per CTA pass
+  const unsigned nslots = (unsigned)(T * heads);
+  const unsigned grid = std::min<unsigned>((nslots + 2 * per - 1) / (2 * per), 148 * 8);
+  rope_kernel<<<grid, threads, 0, s>>>((const bf16*)in, (bf16*)out, (const float2*)cs, nslots, (unsigned)S,
+                                       (unsigned)heads, (unsigned)D, in_stride, out_stride, sign);
+  TFT_CUDA_CHECK(cudaGetLastError());
+}
+
+void rope_qkv_launch(void* packed, size_t row, void* q, void* k, void* v, const int64_t* strides9, const void* cs,
+                     size_t T, int S, int D, int Hq, int Hkv, int dir, cudaStream_t s) {
+  if (D % 8 || D > 2048) throw std::runtime_error("rope_qkv: head_dim must be a multiple of 8 and <= 2048");
+  // v == nullptr: only q and k are produced (forward keeps v as a strided view of the packed projection)
+  const size_t heads = (size_t)Hq + (size_t)Hkv * (v != nullptr ? 2 : 1);
+  if (T * heads >= (1ull << 31)) throw std::runtime_error("rope_qkv: tokens * heads must be < 2^31");
+  if (row != ((size_t)Hq + 2 * (size_t)Hkv) * D) throw std::runtime_error("rope_qkv: packed row must be (Hq + 2 Hkv) * D");
+  if (T == 0) return;
+  RopeQKVArgs a{};
+  a.packed = (bf16*)packed;
+  a.row = row;
+  a.sep[0] = (bf16*)q;
+  a.sep[1] = (bf16*)k;
+  a.sep[2] = (bf16*)v;
+  for (int w = 0; w < 3; ++w) {
+    a.sb[w] = (size_t)strides9[3 * w];
+    a.ss[w] = (size_t)strides9[3 * w + 1];
+    a.sh[w] = (size_t)strides9[3 * w + 2];
+    if ((a.sb[w] | a.ss[w] | a.sh[w]) % 8) throw std::runtime_error("rope_qkv: strides must be multiples of 8 elements");
+  }
+  a.nh[0] = Hq;
+  a.nh[1] = Hkv;
+  a.nh[2] = v != nullptr ? Hkv : 0;
+  a.cs = (const float2*)cs;
+  a.T = (unsigned)T;
+  a.S = (unsigned)S;
+  a.D = (unsigned)D;
+  a.dir = dir;
+  const unsigned vph = D / 8, per = 256 / vph, threads = per * vph;
+  const unsigned nslots = (unsigned)(T * heads);
+  const unsigned grid = std::min<unsigned>((nslots + 2 * per - 1) / (2 * per), 148 * 8);
+  rope_qkv_kernel<<<grid, threads, 0, s>>>(a);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 

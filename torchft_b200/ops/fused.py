@@ -114,23 +114,26 @@ def rope_table(seq_len: int, head_dim: int, theta: float, device: torch.device) 
 class _RoPEQKV(torch.autograd.Function):
     """RoPE on q and k read directly from the fused qkv projection output.
 
-    Returns contiguous (q [B,S,Hq,D], k [B,S,Hkv,D], v [B,S,Hkv,D]) so the
-    rotation doubles as the q/k/v split; backward applies the inverse rotation
-    and writes dq/dk/dv straight into ONE packed d_qkv buffer (no zero-padded
-    slice gradients, no torch.cat).
+    Returns (q [B,S,Hq,D], k [B,S,Hkv,D] contiguous, v [B,S,Hkv,D] as a view of the projection) so the rotation doubles
+    as the q/k/v split: ONE launch. Backward is one launch too: it reads dq/dk/dv in whatever stride order SDPA
+    produced them, applies the inverse rotation and writes ONE packed d_qkv buffer (no zero-padded slice gradients,
+    no torch.cat, no .contiguous()).
     """
 
     @staticmethod
     def forward(ctx, qkv: torch.Tensor, cs: torch.Tensor, B: int, S: int, Hq: int, Hkv: int, D: int):  # type: ignore[override]
         K = _native.load()
         assert qkv.is_contiguous() and qkv.dtype == torch.bfloat16
+        # the kernel reads the table as fp32: a wrapper that down-casts module inputs (FSDP2's cast_forward_inputs) would
+        # make it read garbage and past the end of the buffer
+        assert cs.dtype == torch.float32 and cs.is_contiguous() and cs.shape[0] >= S, "rope table must be the fp32 table of rope_table()"
         row = qkv.shape[-1]
         assert row == (Hq + 2 * Hkv) * D
         q = torch.empty((B, S, Hq, D), dtype=qkv.dtype, device=qkv.device)
         k = torch.empty((B, S, Hkv, D), dtype=qkv.dtype, device=qkv.device)
-        sp = _native.stream_ptr()
-        K.rope(qkv.data_ptr(), q.data_ptr(), cs.data_ptr(), B * S, S, Hq, D, row, Hq * D, 1.0, sp)
-        K.rope(qkv.data_ptr() + 2 * Hq * D, k.data_ptr(), cs.data_ptr(), B * S, S, Hkv, D, row, Hkv * D, 1.0, sp)
+        # one launch rotates q and k out of the packed rows; v stays a strided view of the projection (no copy)
+        K.rope_qkv(qkv.data_ptr(), row, q.data_ptr(), k.data_ptr(), 0, [*q.stride()[:3], *k.stride()[:3], 0, 0, 0],
+                   cs.data_ptr(), B * S, S, D, Hq, Hkv, 0, _native.stream_ptr())
         v = qkv.view(B * S, row)[:, (Hq + Hkv) * D :].reshape(B, S, Hkv, D)
         ctx.save_for_backward(cs)
         ctx.meta = (B, S, Hq, Hkv, D, row)
@@ -141,13 +144,18 @@ class _RoPEQKV(torch.autograd.Function):
         K = _native.load()
         (cs,) = ctx.saved_tensors
         B, S, Hq, Hkv, D, row = ctx.meta
-        dq = dq.contiguous()
-        dk = dk.contiguous()
+
+        def usable(t: torch.Tensor) -> torch.Tensor:
+            # the kernel takes any (batch, position, head) stride order (SDPA hands back [B, H, S, D]-ordered gradients
+            # seen through a transpose) as long as a head vector is contiguous and 16 B aligned
+            ok = t.stride(3) == 1 and all(st % 8 == 0 for st in t.stride()[:3]) and t.data_ptr() % 16 == 0
+            return t if ok else t.contiguous()
+
+        dq, dk, dv = usable(dq), usable(dk), usable(dv)
         dqkv = torch.empty((B * S, row), dtype=dq.dtype, device=dq.device)
-        dqkv[:, (Hq + Hkv) * D :].copy_(dv.reshape(B * S, Hkv * D))
-        sp = _native.stream_ptr()
-        K.rope(dq.data_ptr(), dqkv.data_ptr(), cs.data_ptr(), B * S, S, Hq, D, Hq * D, row, -1.0, sp)
-        K.rope(dk.data_ptr(), dqkv.data_ptr() + 2 * Hq * D, cs.data_ptr(), B * S, S, Hkv, D, Hkv * D, row, -1.0, sp)
+        K.rope_qkv(dqkv.data_ptr(), row, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                   [*dq.stride()[:3], *dk.stride()[:3], *dv.stride()[:3]], cs.data_ptr(), B * S, S, D, Hq, Hkv, 1,
+                   _native.stream_ptr())
         return dqkv, None, None, None, None, None, None
 
 

@@ -64,7 +64,9 @@ class HSDPTrainer:
         torch.manual_seed(seed)
         m = Llama(self.cfg, device=self.device, dtype=torch.float32)
         m.init_weights(seed)
-        mp = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)
+        # cast_forward_inputs=False: the blocks' inputs are the bf16 residual stream and the fp32 RoPE table, which the
+        # RoPE kernel reads as fp32 (the default would hand it a bf16 copy)
+        mp = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32, cast_forward_inputs=False)
         for blk in m.layers:
             fully_shard(blk, mesh=shard_mesh, mp_policy=mp)
         fully_shard(m, mesh=shard_mesh, mp_policy=mp)
