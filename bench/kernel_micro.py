@@ -87,11 +87,13 @@ def main() -> None:
             for tpb in (128, 256, 512):
                 for pf in (0, 1):
                     for cps in (2, 3, 4, 6, 8):
-                        K.rmsnorm_tune(tpb, pf, cps)
+                        K.rmsnorm_tune(0, tpb, pf, cps)
+                        K.rmsnorm_tune(1, tpb, pf, cps)
                         tag = f"t{tpb}_pf{pf}_c{cps}"
                         record("rmsnorm_sweep_fwd_" + tag, timeit(lambda: K.rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), rstd.data_ptr(), T, H, 1e-5, sp()), args.iters, flush), 2 * x.numel() * 2)
                         record("rmsnorm_sweep_bwd_" + tag, timeit(lambda: K.rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), dx.data_ptr(), part.data_ptr(), dw.data_ptr(), False, T, H, sp()), args.iters, flush), 3 * x.numel() * 2)
-            K.rmsnorm_tune(128, 1, 4)
+            K.rmsnorm_tune(0, 128, 1, 6)
+            K.rmsnorm_tune(1, 256, 1, 4)
     if want("swiglu"):
         gu = torch.randn(T, 2 * F, device=dev).bfloat16()
         y = torch.empty(T, F, device=dev, dtype=torch.bfloat16)

@@ -115,7 +115,8 @@ def test_rmsnorm_every_cta_shape_matches_reference(tpb, pf, cps, H):
 
     K = fused._native.load()
     try:
-        K.rmsnorm_tune(tpb, pf, cps)
+        K.rmsnorm_tune(0, tpb, pf, cps)
+        K.rmsnorm_tune(1, tpb, pf, cps)
         torch.manual_seed(5)
         rows = 777
         x = torch.randn(rows, H, device="cuda").bfloat16().requires_grad_()
@@ -128,7 +129,8 @@ def test_rmsnorm_every_cta_shape_matches_reference(tpb, pf, cps, H):
         yf.backward(dy.float())
         assert _rel(y, yf) < 1e-2 and _rel(x.grad, xf.grad) < 1e-2 and _rel(w.grad, wf.grad) < 2e-2
     finally:
-        K.rmsnorm_tune(128, 1, 4)
+        K.rmsnorm_tune(0, 128, 1, 6)
+        K.rmsnorm_tune(1, 256, 1, 4)
 
 
 @pytest.mark.parametrize("T,V", [(64, 1000), (33, 4104), (16, 128256)])

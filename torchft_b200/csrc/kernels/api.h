@@ -83,7 +83,7 @@ void q8_reduce_scatter_launch(const PeerTable& pt, StatusBlock* st, size_t off, 
 void rmsnorm_fwd_launch(const void* x, const void* w, void* y, float* rstd, int rows, int H,
                         float eps, cudaStream_t s);
 int rmsnorm_bwd_grid(int rows);
-void rmsnorm_tune(int tpb, int prefetch, int ctas_per_sm_at_128);
+void rmsnorm_tune(int bwd, int tpb, int prefetch, int ctas_per_sm_at_128);
 void rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                         float* dw_partial, void* dw, int accumulate, int rows, int H,
                         cudaStream_t s, const void* dres = nullptr);

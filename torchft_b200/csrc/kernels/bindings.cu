@@ -356,7 +356,7 @@ PYBIND11_MODULE(_K, m) {
     rmsnorm_fwd_launch(P<void>(x), P<void>(w), P<void>(y), P<float>(rstd), rows, H, eps, S(s));
   });
   m.def("rmsnorm_bwd_grid", &rmsnorm_bwd_grid);
-  m.def("rmsnorm_tune", &rmsnorm_tune, "CTA size (128/256/512), prefetch next row, CTAs/SM at 128 threads");
+  m.def("rmsnorm_tune", &rmsnorm_tune, "(0 forward | 1 backward, CTA size 128/256/512, prefetch next row, CTAs/SM at 128 threads)");
   m.def("rmsnorm_bwd", [](uintptr_t dy, uintptr_t x, uintptr_t w, uintptr_t rstd, uintptr_t dx,
                           uintptr_t dw_partial, uintptr_t dw, bool accumulate, int rows, int H,
                           uintptr_t s, uintptr_t dres) {

@@ -28,7 +28,10 @@ using P8 = Pack<bf16>;
 // SM in flight, which is what HBM3e needs (B200_PROFILING.md: ~40 KB/SM by Little's law); one 512-thread CTA with one
 // vector per thread and three barriers per row (round 1) reached 62 % (fwd) / 43 % (bwd) of the measured copy bandwidth.
 constexpr int kRmsMaxVec = 4;
-static int g_rms_tpb = 128, g_rms_pf = 1, g_rms_cps = 4;
+// {forward, backward}: CTA threads, prefetch, CTAs per SM at 128 threads. Defaults from the B200 sweep at 8192 x 4096
+// (profiles/rmsnorm_sweep_r2.json): forward 128 x 4 vectors, 6 CTAs/SM = 0.77 of the measured copy bandwidth (was 0.61);
+// backward 256 x 2 vectors, 296 CTAs = 0.59 including the column-sum launch (was 0.43).
+static int g_rms_tpb[2] = {128, 256}, g_rms_pf[2] = {1, 1}, g_rms_cps[2] = {6, 4};
 
 template <int TPB>
 __device__ __forceinline__ float row_sum(float v, float (*red)[TPB / 32], int& parity) {
@@ -794,8 +797,8 @@ static int grid_for(size_t work_items, int threads, int cap = 148 * 8) {
 }
 
 // (TPB, NV) for a row of nvec 16 B vectors: the tuned CTA size if NV <= 4 covers the row, else the next larger CTA.
-static void rms_shape(int nvec, int& tpb, int& nv) {
-  for (tpb = g_rms_tpb; tpb <= 512; tpb *= 2) {
+static void rms_shape(int nvec, int bwd, int& tpb, int& nv) {
+  for (tpb = g_rms_tpb[bwd]; tpb <= 512; tpb *= 2) {
     const int need = (nvec + tpb - 1) / tpb;
     nv = need <= 1 ? 1 : need <= 2 ? 2 : 4;
     if (need <= kRmsMaxVec) return;
@@ -803,25 +806,26 @@ static void rms_shape(int nvec, int& tpb, int& nv) {
   tpb = 512;
   nv = kRmsMaxVec;
 }
-static int rms_grid(int rows, int tpb) {
-  const int cap = 148 * std::max(1, g_rms_cps * 128 / tpb);
+static int rms_grid(int rows, int bwd, int tpb) {
+  const int cap = 148 * std::max(1, g_rms_cps[bwd] * 128 / tpb);
   return rows < cap ? rows : cap;
 }
 
-void rmsnorm_tune(int tpb, int prefetch, int ctas_per_sm_at_128) {
+void rmsnorm_tune(int bwd, int tpb, int prefetch, int ctas_per_sm_at_128) {
   if (tpb != 128 && tpb != 256 && tpb != 512) throw std::runtime_error("rmsnorm_tune: tpb must be 128, 256 or 512");
-  g_rms_tpb = tpb;
-  g_rms_pf = prefetch ? 1 : 0;
-  g_rms_cps = std::max(1, ctas_per_sm_at_128);
+  bwd = bwd ? 1 : 0;
+  g_rms_tpb[bwd] = tpb;
+  g_rms_pf[bwd] = prefetch ? 1 : 0;
+  g_rms_cps[bwd] = std::max(1, ctas_per_sm_at_128);
 }
 
-#define RMS_DISPATCH(KERNEL, ...)                                                                          \
+#define RMS_DISPATCH(KERNEL, BWD, ...)                                                                         \
   do {                                                                                                     \
     auto go = [&](auto nvc, auto tpbc, auto pfc) {                                                         \
       KERNEL<decltype(nvc)::value, decltype(tpbc)::value, decltype(pfc)::value><<<grid, tpb, 0, s>>>(__VA_ARGS__); \
     };                                                                                                     \
     auto by_pf = [&](auto nvc, auto tpbc) {                                                                \
-      if (g_rms_pf && !(nv == 4 && tpb == 512)) go(nvc, tpbc, std::true_type{}); else go(nvc, tpbc, std::false_type{}); \
+      if (g_rms_pf[BWD] && !(nv == 4 && tpb == 512)) go(nvc, tpbc, std::true_type{}); else go(nvc, tpbc, std::false_type{}); \
     };                                                                                                     \
     auto by_tpb = [&](auto nvc) {                                                                          \
       if (tpb == 128) by_pf(nvc, std::integral_constant<int, 128>{});                                      \
@@ -837,23 +841,23 @@ void rmsnorm_fwd_launch(const void* x, const void* w, void* y, float* rstd, int 
                         float eps, cudaStream_t s) {
   if (H % 8 || H > 8 * kRmsMaxVec * 512) throw std::runtime_error("rmsnorm: H must be %8 and <= 16384");
   int tpb, nv;
-  rms_shape(H / 8, tpb, nv);
-  const int grid = rms_grid(rows, tpb);
-  RMS_DISPATCH(rmsnorm_fwd_kernel, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
+  rms_shape(H / 8, 0, tpb, nv);
+  const int grid = rms_grid(rows, 0, tpb);
+  RMS_DISPATCH(rmsnorm_fwd_kernel, 0, (const bf16*)x, (const bf16*)w, (bf16*)y, rstd, rows, H, eps);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 
 // rows of the fp32 partial-dw buffer the caller must provide (an upper bound on the grid for any H)
-int rmsnorm_bwd_grid(int rows) { return rms_grid(rows, 128); }
+int rmsnorm_bwd_grid(int rows) { return rms_grid(rows, 1, 128); }
 
 void rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                         float* dw_partial, void* dw, int accumulate, int rows, int H,
                         cudaStream_t s, const void* dres) {
   if (H % 8 || H > 8 * kRmsMaxVec * 512) throw std::runtime_error("rmsnorm: H must be %8 and <= 16384");
   int tpb, nv;
-  rms_shape(H / 8, tpb, nv);
-  const int grid = rms_grid(rows, tpb);
-  RMS_DISPATCH(rmsnorm_bwd_kernel, (const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (bf16*)dx, dw_partial,
+  rms_shape(H / 8, 1, tpb, nv);
+  const int grid = rms_grid(rows, 1, tpb);
+  RMS_DISPATCH(rmsnorm_bwd_kernel, 1, (const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (bf16*)dx, dw_partial,
                (const bf16*)dres, rows, H);
   colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(dw_partial, grid, H, (bf16*)dw, accumulate);
   TFT_CUDA_CHECK(cudaGetLastError());

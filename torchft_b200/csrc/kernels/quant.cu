@@ -180,13 +180,31 @@ __global__ void __launch_bounds__(512) q8_dequantize_kernel(const char* qbuf, si
   const char* payload = qbuf + q8_payload_off(ngroups);
   const int lane = threadIdx.x & 31;
   const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
-  for (size_t g = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups;
-       g += warps) {
-    const size_t e = g * kGroup + lane * 16;
-    if (e >= nelem) continue;
-    float f[16];
-    dequant16(ld_stream(payload + g * kGroup + lane * 16), scales[g], f);
-    store16<T>(out, e, nelem, f);
+  // a warp takes kU groups per pass and issues all their loads before the first use (one 16 B load in flight per lane
+  // measured 69 % of the copy bandwidth in round 1)
+  constexpr int kU = 4;
+  for (size_t g0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g0 < ngroups;
+       g0 += warps * kU) {
+    Vec16 q[kU];
+    float sc[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const size_t g = g0 + u * warps;
+      if (g < ngroups && g * kGroup + lane * 16 < nelem) {
+        q[u] = ld_stream(payload + g * kGroup + lane * 16);
+        sc[u] = scales[g];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const size_t g = g0 + u * warps;
+      const size_t e = g * kGroup + lane * 16;
+      if (g < ngroups && e < nelem) {
+        float f[16];
+        dequant16(q[u], sc[u], f);
+        store16<T>(out, e, nelem, f);
+      }
+    }
   }
 }
 

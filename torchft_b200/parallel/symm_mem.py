@@ -123,6 +123,7 @@ class SymmetricComm:
         self._fdserver: Any = None
         self._peer_vmm: Dict[Tuple[str, int, str], Tuple[int, int, int]] = {}  # (host, pid, seg) -> (va, handle, size)
         self._mc: Dict[str, Tuple[int, int, int]] = {}  # segment -> (mc handle, multicast va, size)
+        self._mc_gen, self._mc_members = "", ""  # creation the objects in _mc belong to / the member list they span
         self._barrier_mode = int(os.environ.get("TORCHFT_B200_BARRIER_MODE", "2"))
         self._force_plan: Optional[Tuple[int, int]] = None  # (algo, blocks) override for tuning sweeps
         self.launches = 0  # native kernel launches issued (bench reports this)
@@ -202,6 +203,7 @@ class SymmetricComm:
                     "floor": self._flag,
                     "mode": self._mode,
                     "fd_server": self._fdserver.name() if self._fdserver is not None else "",
+                    "mc_gen": self._mc_gen,
                     "segments": {n: {"handle": s.handle.hex(), "nbytes": s.nbytes} for n, s in self._segments.items()},
                 }
                 store.set(f"symm/{rank}", json.dumps(desc))
@@ -215,7 +217,6 @@ class SymmetricComm:
                     for n in names:
                         if d["segments"][n]["nbytes"] != self._segments[n].nbytes:
                             raise RuntimeError(f"segment {n!r} size mismatch on rank {r}")
-                self._release_multicast()
                 needed: Dict[Tuple[str, int, bytes], int] = {}
                 needed_vmm: Dict[Tuple[str, int, str], Tuple[int, int, int]] = {}
                 ptrs: Dict[str, List[int]] = {n: [] for n in names}
@@ -262,6 +263,8 @@ class SymmetricComm:
                 self._install(ptrs, rank, world, int(epoch), max(int(d["floor"]) for d in descs))
                 if self._mode == "vmm" and self._nvls_enabled and world > 1 and K.multicast_supported():
                     self._setup_multicast(store, descs, [n for n in names if n != "core"], rank, world)
+                else:
+                    self._release_multicast()
                 self._configured = True
 
     def _install(self, ptrs: Dict[str, List[int]], rank: int, world: int, epoch: int, floor: int,
@@ -337,26 +340,40 @@ class SymmetricComm:
             n = store.add(key, 0)
 
     def _setup_multicast(self, store: Any, descs: List[Dict[str, Any]], names: List[str], rank: int, world: int) -> None:
-        """One NVLS multicast object per user segment over the CURRENT quorum (objects are bound to a
-        fixed device set, so they are re-created -- cheaply -- on every membership change)."""
+        """One NVLS multicast object per user segment over the CURRENT quorum. Objects are bound to a fixed device set,
+        so a membership change re-creates them -- all segments in one round (two store barriers in total, not two per
+        segment) -- and a quorum whose members all still hold the objects of the same earlier creation keeps them."""
         K = self._K
+        members = json.dumps([[d["host"], int(d["pid"])] for d in descs])
+        gens = {d.get("mc_gen", "") for d in descs}
+        if self._mc and len(gens) == 1 and self._mc_gen in gens and self._mc_gen and self._mc_members == members:
+            return  # every rank reports the same live creation over the same members: nothing to rebuild
+        self._release_multicast()
+        gen = f"mc:{self._epoch}:{self._flag}"
+        keys = {n: f"{gen}:{n}" for n in names}
+        mcs: Dict[str, int] = {}
+        if rank == 0:
+            for n in names:
+                mc, fd = K.mc_create(world, self._segments[n].nbytes)
+                self._fdserver.publish(keys[n], fd)
+                mcs[n] = mc
+            store.set("mcready", gen)
+        else:
+            gen = bytes(store.get("mcready")).decode()
+            keys = {n: f"{gen}:{n}" for n in names}
+            for n in names:
+                mcs[n] = K.mc_import(K.fetch_fd(descs[0]["fd_server"], keys[n]))
+        for n in names:
+            K.mc_add_device(mcs[n])
+        self._store_barrier(store, "mcadd", world)
         for n in names:
             seg = self._segments[n]
-            key = f"mc:{n}:{self._epoch}:{self._flag}"
-            if rank == 0:
-                mc, fd = K.mc_create(world, seg.nbytes)
-                self._fdserver.publish(key, fd)
-                store.set(f"mcready/{n}", key)
-            else:
-                key = bytes(store.get(f"mcready/{n}")).decode()
-                mc = K.mc_import(K.fetch_fd(descs[0]["fd_server"], key))
-            K.mc_add_device(mc)
-            self._store_barrier(store, f"mcadd/{n}", world)
-            va = K.mc_bind_and_map(mc, seg.mem_handle, seg.nbytes)
-            self._store_barrier(store, f"mcbind/{n}", world)
-            if rank == 0:
-                self._fdserver.unpublish(key)
-            self._mc[n] = (mc, va, seg.nbytes)
+            self._mc[n] = (mcs[n], K.mc_bind_and_map(mcs[n], seg.mem_handle, seg.nbytes), seg.nbytes)
+        self._store_barrier(store, "mcbind", world)
+        if rank == 0:
+            for n in names:
+                self._fdserver.unpublish(keys[n])
+        self._mc_gen, self._mc_members = gen, members
 
     def _release_multicast(self) -> None:
         for n, (mc, va, size) in list(self._mc.items()):
@@ -365,6 +382,7 @@ class SymmetricComm:
             except Exception:  # noqa: BLE001
                 pass
         self._mc = {}
+        self._mc_gen, self._mc_members = "", ""
 
     # ------------------------------------------------------------- collectives
     def _plan(self, nbytes: int) -> Tuple[int, int]:
