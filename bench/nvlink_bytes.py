@@ -38,13 +38,22 @@ class Counters:
         self.index = index
         self.how = "nvidia-smi"
         self._h = None
+        self.nlinks = 0
         try:
             import pynvml
 
             pynvml.nvmlInit()
             self._nv = pynvml
             self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self._ids = [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX]
+            # scopeId = link index (a bare field id reads link 0 only: round 2's first run counted exactly 1/18 of the
+            # algorithmic bytes that way); ask the device how many links it has and sum them
+            try:
+                nlinks = int(pynvml.nvmlDeviceGetFieldValues(self._h, [pynvml.NVML_FI_DEV_NVLINK_LINK_COUNT])[0].value.uiVal)
+            except Exception:
+                nlinks = 0
+            self.nlinks = nlinks if 0 < nlinks <= pynvml.NVML_NVLINK_MAX_LINKS else pynvml.NVML_NVLINK_MAX_LINKS
+            self._ids = [(f, l) for l in range(self.nlinks) for f in (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX,
+                                                                     pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX)]
             tx, rx = self._nvml()
             if tx >= 0:
                 self.how = "nvml_field_values"
@@ -55,12 +64,17 @@ class Counters:
 
     def _nvml(self):
         vals = self._nv.nvmlDeviceGetFieldValues(self._h, self._ids)
-        out = []
-        for v in vals:
+        tx = rx = 0
+        good = 0
+        for i, v in enumerate(vals):
             if v.nvmlReturn != 0:
-                return -1, -1
-            out.append(int(v.value.ullVal) * 1024)
-        return out[0], out[1]
+                continue  # inactive link
+            good += 1
+            if i % 2 == 0:
+                tx += int(v.value.ullVal) * 1024
+            else:
+                rx += int(v.value.ullVal) * 1024
+        return (tx, rx) if good else (-1, -1)
 
     def read(self):
         if self._h is not None:
@@ -132,7 +146,7 @@ def main() -> None:
         torch.cuda.synchronize()
         dist.barrier()
 
-    res = {"world": W, "input_mb": round(S / 2**20, 1), "replication": k, "counter_source": ctr.how, "iters": a.iters, "ops": {}}
+    res = {"world": W, "input_mb": round(S / 2**20, 1), "replication": k, "counter_source": ctr.how, "links_summed": ctr.nlinks, "iters": a.iters, "ops": {}}
     for name, (fn, alg_rx, alg_tx) in ops.items():
         if W == 1:
             break

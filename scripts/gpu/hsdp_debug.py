@@ -22,7 +22,15 @@ backend = sys.argv[2] if len(sys.argv) > 2 else "b200"
 lh = local_lighthouse()
 tr = HSDPTrainer(model, loopback(lh.address()), shards=1, backend=backend, timeout=timedelta(seconds=30))
 cfg = tr.cfg
-S = min(cfg.max_seq_len, 512)
+S = min(cfg.max_seq_len, int(os.environ.get("HSDP_DEBUG_SEQ", "512")))
+
+
+def mem(tag):
+    torch.cuda.synchronize()
+    print(f"   [mem] {tag}: allocated {torch.cuda.memory_allocated() / 2**30:.2f} GiB, peak {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB", flush=True)
+
+
+mem(f"after build ({sum(p.numel() for p in tr.model.parameters()) / 1e9:.2f} B params)")
 tok = torch.randint(0, cfg.vocab_size, (2, S), device="cuda")
 tgt = torch.randint(0, cfg.vocab_size, (2, S), device="cuda")
 
@@ -35,14 +43,15 @@ losses = []
 for i in range(3):
     tr.optim.zero_grad(set_to_none=True)
     loss = tr.model(tok, tgt)
+    mem("after forward")
     loss.backward()
-    torch.cuda.synchronize()
+    mem("after backward")
     bad = [(n, str(local(p.grad).dtype)) for n, p in tr.model.named_parameters() if p.grad is not None and not torch.isfinite(local(p.grad)).all()]
     none = [n for n, p in tr.model.named_parameters() if p.grad is None]
     gmax = max(float(local(p.grad).abs().max()) for p in tr.model.parameters() if p.grad is not None)
     print(f"step {i} loss {float(loss.detach()):.4f} non-finite grads: {bad[:8]} none: {none[:4]} gmax {gmax:.3e}", flush=True)
     tr.optim.step()
-    torch.cuda.synchronize()
+    mem("after optimizer step")
     badp = [n for n, p in tr.model.named_parameters() if not torch.isfinite(local(p.data)).all()]
     print(f"   committed {tr.manager.current_step()} non-finite params after step: {badp[:8]}", flush=True)
     losses.append(float(loss.detach()))
