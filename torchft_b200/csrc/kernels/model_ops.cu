@@ -212,32 +212,34 @@ __global__ void __launch_bounds__(TPB) rmsnorm_bwd_kernel(
   }
 }
 
-// dw[h] (+)= sum_b partial[b][h]: a CTA owns 32 columns, its 8 warps stride over the partial rows (each warp load is one
-// 128 B line), then the 8 per-warp sums meet in shared memory.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ partial, int nb, int H,
-                                                     bf16* __restrict__ dw, int accumulate) {
-  __shared__ float acc[8][33];
+// dw[h] (+)= sum_b partial[b][h]: a CTA owns 32 columns; its 32 warps stride over the partial rows (a warp load is one
+// 128 B line, up to 8 independent loads in flight per lane), then the 32 per-warp sums meet in shared memory. ncu of the
+// first version (8 warps, 4 loads in flight, 37 dependent rounds): 11.4 us for 4.9 MB -- a quarter of the whole backward.
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ partial, int nb, int H,
+                                                      bf16* __restrict__ dw, int accumulate) {
+  __shared__ float acc[32][33];
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int h = blockIdx.x * 32 + lane;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float s = 0.f;
   if (h < H) {
     int b = wrp;
-    for (; b + 24 < nb; b += 32) {
-      s0 += partial[(size_t)b * H + h];
-      s1 += partial[(size_t)(b + 8) * H + h];
-      s2 += partial[(size_t)(b + 16) * H + h];
-      s3 += partial[(size_t)(b + 24) * H + h];
+    for (; b + 7 * 32 < nb; b += 8 * 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(partial + (size_t)(b + u * 32) * H + h);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
     }
-    for (; b < nb; b += 8) s0 += partial[(size_t)b * H + h];
+    for (; b < nb; b += 32) s += __ldcs(partial + (size_t)b * H + h);
   }
-  acc[wrp][lane] = (s0 + s1) + (s2 + s3);
+  acc[wrp][lane] = s;
   __syncthreads();
   if (wrp == 0 && h < H) {
-    float s = 0.f;
+    float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += acc[i][lane];
-    if (accumulate) s += __bfloat162float(dw[h]);
-    dw[h] = __float2bfloat16(s);
+    for (int i = 0; i < 32; ++i) t += acc[i][lane];
+    if (accumulate) t += __bfloat162float(dw[h]);
+    dw[h] = __float2bfloat16(t);
   }
 }
 
@@ -859,7 +861,7 @@ void rmsnorm_bwd_launch(const void* dy, const void* x, const void* w, const floa
   const int grid = rms_grid(rows, 1, tpb);
   RMS_DISPATCH(rmsnorm_bwd_kernel, 1, (const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (bf16*)dx, dw_partial,
                (const bf16*)dres, rows, H);
-  colsum_kernel<<<(H + 31) / 32, 256, 0, s>>>(dw_partial, grid, H, (bf16*)dw, accumulate);
+  colsum_kernel<<<(H + 31) / 32, 1024, 0, s>>>(dw_partial, grid, H, (bf16*)dw, accumulate);
   TFT_CUDA_CHECK(cudaGetLastError());
 }
 

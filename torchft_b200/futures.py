@@ -30,24 +30,29 @@ WATCHDOG_TIMEOUT_SEC_ENV = "TORCHFT_WATCHDOG_TIMEOUT_SEC"
 
 
 class _Handle:
-    """Cancellable timer entry."""
+    """Cancellable timer entry. It owns the callback so that ``cancel()`` can drop it at once: the heap entry itself only
+    leaves the heap at its deadline, and a callback closure typically references the future being guarded (and through
+    it the result tensor) -- kept until the deadline, every collective of every step would pin its tensor for a full op
+    timeout (FSDP2 hands the manager a fresh gradient shard per parameter group per step: 16 GB per step at 8B)."""
 
-    __slots__ = ("cancelled", "fired")
+    __slots__ = ("cancelled", "fired", "cb")
 
-    def __init__(self) -> None:
+    def __init__(self, cb: Optional[Callable[[], None]] = None) -> None:
         self.cancelled = False
         self.fired = False
+        self.cb = cb
 
     def cancel(self) -> None:
         self.cancelled = True
+        self.cb = None
 
 
 class _TimeoutManager:
-    """One daemon thread, one heap of (deadline, seq, handle, callback)."""
+    """One daemon thread, one heap of (deadline, seq, handle); the handle carries the callback."""
 
     def __init__(self) -> None:
         self._cv = threading.Condition()
-        self._heap: List[Tuple[float, int, _Handle, Callable[[], None]]] = []
+        self._heap: List[Tuple[float, int, _Handle]] = []
         self._seq = itertools.count()
         self._thread: Optional[threading.Thread] = None
         self._watchdog: Optional[threading.Thread] = None
@@ -89,8 +94,9 @@ class _TimeoutManager:
                 now = time.monotonic()
                 due: List[Tuple[_Handle, Callable[[], None]]] = []
                 while self._heap and self._heap[0][0] <= now:
-                    _, _, h, cb = heapq.heappop(self._heap)
-                    if not h.cancelled:
+                    _, _, h = heapq.heappop(self._heap)
+                    cb = h.cb
+                    if not h.cancelled and cb is not None:
                         due.append((h, cb))
                 if not due:
                     wait = 1.0
@@ -100,6 +106,7 @@ class _TimeoutManager:
                     continue
             for h, cb in due:
                 h.fired = True
+                h.cb = None
                 try:
                     cb()
                 except Exception:  # pragma: no cover - callbacks must not kill the thread
@@ -126,9 +133,9 @@ class _TimeoutManager:
     # -- api ---------------------------------------------------------------
     def call_later(self, timeout: timedelta, cb: Callable[[], None]) -> _Handle:
         self._ensure_started()
-        h = _Handle()
+        h = _Handle(cb)
         with self._cv:
-            heapq.heappush(self._heap, (time.monotonic() + timeout.total_seconds(), next(self._seq), h, cb))
+            heapq.heappush(self._heap, (time.monotonic() + timeout.total_seconds(), next(self._seq), h))
             self._cv.notify_all()
         return h
 
