@@ -42,6 +42,8 @@ def local(t):
 losses = []
 for i in range(3):
     tr.optim.zero_grad(set_to_none=True)
+    if getattr(tr, "_grad_arena", None) is not None:
+        tr._grad_arena.begin_step()
     loss = tr.model(tok, tgt)
     mem("after forward")
     loss.backward()
@@ -60,4 +62,8 @@ assert losses[-1] < losses[0], losses  # same batch every step: the loss must go
 tr.shutdown()
 lh.shutdown()
 dist.destroy_process_group()
+arena = getattr(tr, "_grad_arena", None)
+if arena is not None:
+    print(f"symmetric gradient arena: {arena._arena.numel() / 2**20:.1f} MiB, used {arena._off / 2**20:.1f} MiB, fallbacks {arena.fallbacks}")
+    assert arena.fallbacks == 0 and arena._off > 0
 print("HSDP_DEBUG ok")

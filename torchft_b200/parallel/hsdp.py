@@ -23,6 +23,47 @@ import torch.distributed as dist
 from torch.distributed import TCPStore
 
 
+class SymmetricShardGrads:
+    """FSDP2 reduce-scatter communicator (``FSDPModule.set_custom_reduce_scatter``) whose OUTPUT buffers -- the fp32
+    gradient shards that FSDP2 then hands to the cross-replica all-reduce hook and finally installs as ``param.grad`` --
+    are carved out of one NVLink-symmetric arena of ``ProcessGroupB200``. The cross-replica all-reduce of a shard is then
+    the zero-copy in-place kernel over peer memory (same arena offset on every replica group: backward visits the FSDP
+    groups in the same order everywhere) instead of staging 2 x 436 MB per block through the 256 MB bounce buffer.
+
+    The arena is a bump allocator: ``begin_step()`` (before backward) rewinds it; it must hold one step's worth of
+    gradient shards (they stay alive until the optimizer has consumed them). The reduce-scatter INPUT stays an ordinary
+    allocation, and the reduce-scatter itself is the stock intra-group collective."""
+
+    def __init__(self, arena: torch.Tensor) -> None:
+        self._arena = arena  # uint8, symmetric
+        self._off = 0
+        self._want_output = False
+        self.fallbacks = 0
+
+    def begin_step(self) -> None:
+        self._off = 0
+        self._want_output = False
+
+    def allocate(self, size: Any, *, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+        # FSDP2 (foreach_reduce) allocates strictly input, output, input, output, ...
+        is_output, self._want_output = self._want_output, not self._want_output
+        if is_output:
+            n = 1
+            for d in size:
+                n *= int(d)
+            nbytes = n * torch.empty((), dtype=dtype).element_size()
+            lo = (self._off + 255) // 256 * 256
+            if lo + nbytes <= self._arena.numel():
+                self._off = lo + nbytes
+                return self._arena[lo:lo + nbytes].view(dtype).view(*[int(d) for d in size])
+            self.fallbacks += 1  # arena too small (gradient accumulation over several backwards): staged path
+        return torch.empty(*size, dtype=dtype, device=device)
+
+    def __call__(self, output_tensor: torch.Tensor, input_tensor: torch.Tensor, group: dist.ProcessGroup, op: Any,
+                 async_op: bool = False) -> Any:
+        return dist.reduce_scatter_tensor(output=output_tensor, input=input_tensor, group=group, op=op, async_op=async_op)
+
+
 class HSDPTrainer:
     """Llama over ``groups x shards`` GPUs.
 
@@ -76,10 +117,15 @@ class HSDPTrainer:
             from torchft_b200.parallel.process_group_b200 import ProcessGroupB200
 
             self.pg: Any = ProcessGroupB200(timeout=timeout, device=self.device)
+            # one step's fp32 gradient shards live in symmetric memory (see SymmetricShardGrads); 256 B per FSDP group
+            # of alignment slack
+            shard_bytes = sum(-(-p.numel() // shards) for p in m.parameters()) * 4 + 256 * (len(m.layers) + 2) + (1 << 20)
+            self._grad_arena: Optional[SymmetricShardGrads] = SymmetricShardGrads(self.pg.alloc_symmetric("hsdp_grads", shard_bytes))
         else:
             from torchft_b200.process_group import ProcessGroupNCCL
 
             self.pg = ProcessGroupNCCL(timeout=timeout)
+            self._grad_arena = None
         self.manager = Manager(pg=self.pg, load_state_dict=None, state_dict=None, min_replica_size=self.groups,
                                timeout=timeout, quorum_timeout=timeout, connect_timeout=timeout, rank=self.group_rank,
                                world_size=shards, store_addr="127.0.0.1", store_port=int(port[0]),
@@ -94,6 +140,8 @@ class HSDPTrainer:
         for mod in m.modules():
             if hasattr(mod, "set_all_reduce_hook"):
                 mod.set_all_reduce_hook(cross_replica)
+                if self._grad_arena is not None:
+                    mod.set_custom_reduce_scatter(self._grad_arena)
         self.inner = torch.optim.AdamW(m.parameters(), lr=lr, betas=(0.9, 0.95), weight_decay=0.1, fused=True)
         self.optim = Optimizer(self.manager, self.inner)
         self._tok: Optional[torch.Tensor] = None
@@ -105,6 +153,8 @@ class HSDPTrainer:
 
     def step_device(self, tokens: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         self.optim.zero_grad(set_to_none=True)   # start_quorum (async)
+        if self._grad_arena is not None:
+            self._grad_arena.begin_step()        # last step's gradient shards are gone: rewind the symmetric arena
         loss = self.model(tokens, targets)
         loss.backward()                          # FSDP reduce-scatter + cross-replica hook per block, overlapped
         self.optim.step()                        # should_commit (AND over the group's ranks), then AdamW on the shards
