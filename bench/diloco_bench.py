@@ -93,6 +93,7 @@ def main() -> None:
                "inner_step_ms": round(float(t[1]), 2), "sync_step_ms": round(float(t[2]), 2),
                "outer_sync_overhead_ms": round(float(t[2] - t[1]), 2), "outer_steps_committed": manager.current_step(),
                "pseudo_grad_bytes": nparam * 2, "flat_fast_path": not a.no_flat,
+               "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2**30, 1),
                "link_time_ms_at_770GBps": round((nparam * (1 if a.quantize else 2)) * 2 * (world - 1) / world / 770e6, 2)}
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
         with open(a.out, "a") as f:

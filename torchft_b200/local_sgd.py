@@ -26,6 +26,7 @@ from __future__ import annotations
 import logging
 import math
 import os
+import time
 from contextlib import nullcontext
 from types import TracebackType
 from typing import Any, Dict, List, Optional, Tuple, Type
@@ -43,6 +44,19 @@ except Exception:  # pragma: no cover
     DTensor = None  # type: ignore[assignment,misc]
 
 logger = logging.getLogger(__name__)
+_TRACE = os.environ.get("TORCHFT_B200_DILOCO_TRACE", "0") == "1"  # print the duration of every phase of an outer sync
+
+
+def _trace(tag: str, t0: float) -> float:
+    """With TORCHFT_B200_DILOCO_TRACE=1: drain the device, print the time since ``t0``, return the new origin."""
+    if not _TRACE:
+        return t0
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    print(f"[diloco trace] {tag}: {(t1 - t0) * 1e3:.2f} ms", flush=True)
+    return t1
+
 
 USE_BUCKETIZATION_ENV = "TORCHFT_USE_BUCKETIZATION"
 
@@ -494,7 +508,9 @@ class _StreamingDiLoCoFragment:
         from torchft_b200.ops import _native
 
         assert self._flat_param is not None and self._flat_orig is not None and self._flat_mom is not None
+        t0 = _trace("   all-reduce waited", time.perf_counter())
         should_commit = self._manager.should_commit()
+        t0 = _trace("   should_commit", t0)
         with torch.no_grad():
             if should_commit:
                 g = self._outer_optimizer.param_groups[0]
@@ -593,12 +609,15 @@ class DiLoCo:
         self._manager.allow_state_dict_read()
         self._local_step += 1
 
+        t0 = _trace("inner step drained", time.perf_counter()) if self._local_step >= self._sync_every - self._fragment_sync_delay else 0.0
         if self._local_step == self._sync_every - self._fragment_sync_delay:
             # sync quorum: blocks, heals eagerly; every replica then prepares the SAME fragment
             self._manager.start_quorum()
+            t0 = _trace("start_quorum (synchronous)", t0)
             frag = self._current_fragment()
             logger.info(f"Preparing fragment={frag} step={self._local_step}")
             self._fragments[frag].prepare_sync()
+            t0 = _trace("prepare_sync (pseudo-gradient all-reduce enqueued + drained)", t0)
 
         if self._local_step < self._sync_every:
             return
@@ -606,5 +625,6 @@ class DiLoCo:
         frag = self._current_fragment()
         logger.info(f"Syncing fragment={frag} step={self._local_step} manager_step={self._manager.current_step()}")
         self._fragments[frag].perform_sync()
+        _trace("perform_sync (wait + should_commit + outer step)", t0)
         # on failure the parameters were reset to the last global copy; the window is retried
         self._local_step = 0
