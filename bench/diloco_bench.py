@@ -85,13 +85,21 @@ def main() -> None:
                 (sync_ms if (i + 1) % a.sync_every == 0 else step_ms).append(s.elapsed_time(e))
     window_ms = sum(step_ms) / len(step_ms) * (a.sync_every - 1) + sum(sync_ms) / len(sync_ms)
     t = torch.tensor([window_ms, sum(step_ms) / len(step_ms), sum(sync_ms) / len(sync_ms)], dtype=torch.float64)
+    # replicas run their inner steps unsynchronised, so at the sync the fast ones WAIT for the slowest (GPU clocks differ by a
+    # few % under the power cap: ~1 s after 100 steps of 390 ms). The slowest replica arrives last and waits for nobody:
+    # MIN over ranks of (sync step - own inner step) is the cost of the sync itself, MAX - MIN is straggler wait.
+    own = torch.tensor([t[2] - t[1]], dtype=torch.float64)
+    lo = own.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         nparam = cfg.num_params()
         res = {"model": a.model, "params_b": round(nparam / 1e9, 3), "world": world, "seq": a.seq, "sync_every": a.sync_every,
                "quantize": a.quantize, "tokens_per_s": round(world * a.seq * a.sync_every / float(t[0]) * 1e3, 1),
                "inner_step_ms": round(float(t[1]), 2), "sync_step_ms": round(float(t[2]), 2),
-               "outer_sync_overhead_ms": round(float(t[2] - t[1]), 2), "outer_steps_committed": manager.current_step(),
+               "outer_sync_overhead_ms": round(float(t[2] - t[1]), 2),
+               "outer_sync_cost_ms_slowest_replica": round(float(lo[0]), 2),
+               "straggler_wait_ms_fastest_replica": round(float(t[2] - t[1]) - float(lo[0]), 2), "outer_steps_committed": manager.current_step(),
                "pseudo_grad_bytes": nparam * 2, "flat_fast_path": not a.no_flat,
                "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2**30, 1),
                "link_time_ms_at_770GBps": round((nparam * (1 if a.quantize else 2)) * 2 * (world - 1) / world / 770e6, 2)}
