@@ -158,6 +158,17 @@ def main() -> None:
         off += mine.numel()
         check("reduce_scatter_quantized", ((got_q - mine).abs().mean() / mine.abs().mean()).item() <= 0.05)
 
+    # ---- a symmetric segment allocated AFTER the first quorum: ordinary memory (staged path) until the next quorum change,
+    # zero-copy from then on; the last rank allocates it only after that reconfigure -> still staged, still correct ----
+    late = None
+    if rank != world - 1 or world == 1:
+        late = pg.alloc_symmetric("late", 1 << 20).view(torch.float32)
+    check("late_segment_not_symmetric_yet", late is None or not pg.comm.is_symmetric("late"))
+    v = late[:4096] if late is not None else torch.empty(4096, device=dev)
+    v.fill_(float(rank + 1))
+    ar(v, ReduceOp.SUM)
+    check("late_segment_allreduce_staged", bool((v == sum(range(1, world + 1))).all()))
+
     check("no_sidecar", pg._sidecar is None)
     check("no_latched_error", pg.errored() is None, err=str(pg.errored()))
 
@@ -168,6 +179,22 @@ def main() -> None:
     z = torch.ones(1 << 16, device=dev)
     ar(z, ReduceOp.SUM)
     check("post_reconfigure", bool((z == world).all()) and pg.errored() is None)
+    # the last rank never registered "late": the segment stays local-only on everybody (intersection rule) and works
+    check("late_segment_needs_every_rank", late is None or pg.comm.is_symmetric("late") == (world == 1))
+    v = late[:4096] if late is not None else torch.empty(4096, device=dev)
+    v.fill_(2.0)
+    ar(v, ReduceOp.SUM)
+    check("late_segment_allreduce_after_reconfigure", bool((v == 2.0 * world).all()))
+    if world > 1 and rank == world - 1:
+        late = pg.alloc_symmetric("late", 1 << 20).view(torch.float32)
+    dist.barrier()
+    pg.configure(f"{store_addr}/pgtest/3", f"r{rank}", rank, world, quorum_id=3)
+    check("late_segment_symmetric_once_everybody_has_it", pg.comm.is_symmetric("late"))
+    before = pg.comm.launches
+    v = late[:4096]
+    v.fill_(3.0)
+    ar(v, ReduceOp.SUM)
+    check("late_segment_allreduce_zero_copy", bool((v == 3.0 * world).all()) and pg.comm.launches - before == 1)
     dist.barrier()
     took = 0.0
     if rank == world - 1:

@@ -164,19 +164,22 @@ class SymmetricComm:
     def alloc(self, name: str, nbytes: int) -> torch.Tensor:
         """Allocate a symmetric (peer-visible) segment; returns a uint8 tensor.
 
-        Must be called with the same ``name``/``nbytes`` on every replica before the
-        next ``configure()``; tensors carved from it are all-reduced zero-copy.
+        Call with the same ``name``/``nbytes`` on every replica. Peers learn about segments at ``configure()``: a
+        segment becomes symmetric (zero-copy collectives, peer pointers) at the first quorum in which EVERY rank has it.
+        Allocating after the group was configured is allowed; until the next quorum change tensors carved from the new
+        segment are ordinary device memory to the collectives (they go through the staging buffer) and
+        :meth:`is_symmetric` says so. Code that NEEDS peer pointers (FT-ZeRO-1) allocates before the first quorum.
         """
         with self._lock:
             self._ensure_core()
             if name in self._segments:
                 raise ValueError(f"symmetric segment {name!r} already exists")
-            if self._configured:
-                # peers learn about segments at configure(); adding one now would leave this rank
-                # unusable until the NEXT quorum change, so refuse loudly instead
-                raise RuntimeError("allocate symmetric segments before the group is configured (before the first quorum)")
             seg = self._alloc_segment(name, nbytes)
             return seg.tensor[:nbytes]
+
+    def is_symmetric(self, name: str) -> bool:
+        """True once segment ``name`` is mapped by (and from) every rank of the current quorum."""
+        return name in self._tables
 
     def set_timeout(self, timeout: timedelta) -> None:
         self._timeout = timeout
@@ -210,13 +213,19 @@ class SymmetricComm:
                 descs: List[Dict[str, Any]] = []
                 for r in range(world):
                     descs.append(desc if r == rank else json.loads(bytes(store.get(f"symm/{r}")).decode()))
-                names = sorted(self._segments)
+                # symmetric = registered by EVERY rank of this quorum (a replica may have allocated a segment after its
+                # peers' last configure, or not yet): the rest stays local-only until a later quorum
+                names = sorted(n for n in self._segments if all(n in d["segments"] for d in descs))
+                if "core" not in names:
+                    raise RuntimeError("a quorum member has no core segment")
                 for r, d in enumerate(descs):
-                    if sorted(d["segments"]) != names:
-                        raise RuntimeError(f"rank {r} registered segments {sorted(d['segments'])}, expected {names}")
                     for n in names:
                         if d["segments"][n]["nbytes"] != self._segments[n].nbytes:
                             raise RuntimeError(f"segment {n!r} size mismatch on rank {r}")
+                late = sorted(set(self._segments) - set(names))
+                if late:
+                    logger.warning("symmetric segments %s are not registered on every replica yet: staged path until "
+                                   "the next quorum change", late)
                 needed: Dict[Tuple[str, int, bytes], int] = {}
                 needed_vmm: Dict[Tuple[str, int, str], Tuple[int, int, int]] = {}
                 ptrs: Dict[str, List[int]] = {n: [] for n in names}
@@ -419,10 +428,11 @@ class SymmetricComm:
         return f
 
     def _segment_of(self, t: torch.Tensor) -> Optional[Tuple[Segment, int]]:
+        """(segment, byte offset) if ``t`` lives in a segment that is mapped on every rank of the current quorum."""
         p, n = t.data_ptr(), t.numel() * t.element_size()
         for s in self._segments.values():
             if s.contains(p, n):
-                return s, p - s.ptr
+                return (s, p - s.ptr) if s.name in self._tables else None
         return None
 
     def allreduce_(self, t: torch.Tensor, op: int = _native.OP_SUM, scale: float = 1.0,
@@ -510,7 +520,7 @@ class SymmetricComm:
             q_bytes = (self._K.q8_buffer_bytes(n, self._world) + 255) // 256 * 256
             need = q_bytes + self._K.q8_slice_buffer_bytes(n, self._world)
             for name, seg in self._segments.items():
-                if name.endswith("_q8") and seg.nbytes >= need:
+                if name.endswith("_q8") and seg.nbytes >= need and name in self._tables:
                     table = self._tables[name]
                     ngroups = self._K.q8_ngroups(n, self._world)
                     big = max(1, min(148 * 16, ngroups // 16 + 1))

@@ -243,6 +243,11 @@ class Zero1Optimizer:
     def _on_configured(self, store: Any, rank: int, world: int, epoch: int) -> None:
         """Runs inside ``ProcessGroupB200.configure`` (quorum thread) with the quorum-scoped store."""
         with self._lock:
+            missing = [n for n in ("z1_param", "z1_grad", "z1_master", "z1_m", "z1_v") if not self.comm.is_symmetric(n)]
+            if missing:
+                # the kernels dereference peer pointers: every replica must construct its Zero1Optimizer before its first
+                # quorum (segments allocated later only become symmetric at the NEXT quorum change)
+                raise RuntimeError(f"FT-ZeRO-1 segments {missing} are not mapped on every replica of this quorum")
             me = {"t": self.t, "hold": self._holdings}
             store.set(f"z1/{rank}", json.dumps(me))
             peers: Dict[int, Dict[str, Any]] = {rank: me}
