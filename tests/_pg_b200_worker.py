@@ -103,6 +103,15 @@ def main() -> None:
     torch.cuda.synchronize()
     check("alltoall_base", torch.equal(a_out, torch.cat([torch.arange(rank * 50, (rank + 1) * 50, device=dev, dtype=torch.int32) + 10000 * p for p in range(world)])))
 
+    # unequal splits: rank r sends (r + p + 1) rows of 3 int64 to rank p, every row tagged with (sender, destination)
+    in_rows = [rank + p + 1 for p in range(world)]
+    out_rows = [p + rank + 1 for p in range(world)]
+    v_in = torch.cat([torch.full((in_rows[p], 3), 1000 * rank + p, device=dev, dtype=torch.int64) for p in range(world)])
+    v_out = torch.full((sum(out_rows), 3), -1, device=dev, dtype=torch.int64)
+    pg.alltoall_base(v_out, v_in, out_rows, in_rows, AllToAllOptions()).wait()
+    torch.cuda.synchronize()
+    check("alltoall_base_unequal_splits", torch.equal(v_out, torch.cat([torch.full((out_rows[p], 3), 1000 * p + rank, device=dev, dtype=torch.int64) for p in range(world)])))
+
     # ring send/recv (both posted before either is waited on: sends and receives run on separate streams)
     msg = torch.full((200_000,), float(rank), device=dev)
     got = torch.empty_like(msg)

@@ -378,8 +378,19 @@ class ProcessGroupB200(ProcessGroup):
                  and input_buffer.numel() * input_buffer.element_size() == output_buffer.numel() * output_buffer.element_size())
         if equal and self._raw_ok(output_buffer) and self._raw_ok(input_buffer):
             return self._launch(lambda s: self._comm.alltoall_(output_buffer, input_buffer, stream=s), output_buffer)
-        # unequal splits: a rank only knows its own row and column of the split matrix, so the ranks cannot agree on
-        # the number of staging rounds without an extra exchange -- left to the library path
+        if self._raw_ok(output_buffer) and self._raw_ok(input_buffer) and output_buffer.dim() >= 1 and input_buffer.dim() >= 1:
+            # unequal splits (in rows of dim 0): the ranks agree on the number of staging rounds with one tiny MAX
+            # all-reduce, then run the same push exchange with per-peer lengths
+            def rows_to_bytes(buf: torch.Tensor, splits: List[int]) -> List[int]:
+                row = (buf.numel() // max(buf.shape[0], 1)) * buf.element_size()
+                if not splits:
+                    assert buf.shape[0] % w == 0, "alltoall_base: dim 0 must divide by the world size when no splits are given"
+                    splits = [buf.shape[0] // w] * w
+                assert len(splits) == w and sum(splits) == buf.shape[0], "alltoall_base: splits must cover dim 0"
+                return [int(x) * row for x in splits]
+
+            ob, ib = rows_to_bytes(output_buffer, output_split_sizes), rows_to_bytes(input_buffer, input_split_sizes)
+            return self._launch(lambda s: self._comm.alltoallv_(output_buffer, input_buffer, ob, ib, stream=s), output_buffer)
         return self._get_sidecar().alltoall_base(output_buffer, input_buffer, output_split_sizes, input_split_sizes, opts)
 
     def _p2p_launch(self, stream: torch.cuda.Stream, fn: Any, tensors: List[torch.Tensor]) -> Work:

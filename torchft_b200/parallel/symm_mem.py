@@ -20,6 +20,7 @@ the analogue of ``ncclCommAbort`` without tearing anything down.
 from __future__ import annotations
 
 import json
+import contextlib
 import logging
 import os
 import socket
@@ -573,13 +574,17 @@ class SymmetricComm:
     def _xblocks(self, nbytes: int) -> int:
         return max(1, min(self._max_blocks, self._K.MAX_BLOCKS, nbytes // (64 << 10)))
 
-    def _exchange(self, inp: int, out: int, send: List[Tuple[int, int]], recv: List[Tuple[int, int]], stream: Any) -> None:
+    def _exchange(self, inp: int, out: int, send: List[Tuple[int, int]], recv: List[Tuple[int, int]], stream: Any,
+                  rounds: Optional[int] = None) -> None:
         """One push-exchange launch per staging round. ``send[p] = (offset, bytes)`` into ``inp`` owed to rank p,
-        ``recv[p] = (offset, bytes)`` into ``out`` expected from rank p. Every rank must derive the same number of
-        rounds, i.e. callers only pass messages whose length is known quorum-wide."""
+        ``recv[p] = (offset, bytes)`` into ``out`` expected from rank p. Every rank must run the same number of
+        rounds: either the message lengths are known quorum-wide (default: derived from them) or the caller agreed on
+        ``rounds`` beforehand (:meth:`alltoallv_`)."""
         W = self._world
         stride = (self._staging_usable // W) & ~15
         longest = max([n for _, n in send] + [n for _, n in recv] + [0])
+        if rounds is not None:
+            longest = rounds * stride
         if longest == 0:
             return
         sp = _native.stream_ptr(stream)
@@ -643,6 +648,38 @@ class SymmetricComm:
                 return
             c = nb // W
             self._exchange(inp.data_ptr(), out.data_ptr(), [(p * c, c) for p in range(W)], [(p * c, c) for p in range(W)], stream)
+
+    def alltoallv_(self, out: torch.Tensor, inp: torch.Tensor, out_bytes: List[int], in_bytes: List[int],
+                   stream: Optional[torch.cuda.Stream] = None) -> None:
+        """All-to-all with per-peer lengths: the first ``in_bytes[p]`` ... bytes of ``inp`` (consecutive chunks) go to rank
+        p, which stores what it gets from rank q as its q-th consecutive chunk of ``out_bytes[q]`` bytes. A rank only
+        knows its own row and column of the split matrix, so the ranks first agree on the number of staging rounds with
+        one 16-byte MAX all-reduce that is read back on the host (a synchronisation: this is not a hot-path collective)."""
+        self._check_raw(out, inp)
+        with self._lock:
+            if not self._configured:
+                raise RuntimeError("SymmetricComm is not configured")
+            W = max(self._world, 1)
+            if len(out_bytes) != W or len(in_bytes) != W:
+                raise ValueError("alltoallv_: one length per rank")
+            if sum(in_bytes) > inp.numel() * inp.element_size() or sum(out_bytes) > out.numel() * out.element_size():
+                raise ValueError("alltoallv_: splits exceed the buffers")
+            if W == 1:
+                out.view(-1).view(torch.uint8)[: in_bytes[0]].copy_(inp.view(-1).view(torch.uint8)[: in_bytes[0]])
+                return
+            stride = (self._staging_usable // W) & ~15
+            mine = (max(list(in_bytes) + list(out_bytes)) + stride - 1) // stride
+            with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
+                agree = torch.tensor([float(mine), 0.0, 0.0, 0.0], dtype=torch.float32, device=self.device)
+            self.allreduce_(agree, op=_native.OP_MAX, stream=stream)
+            rounds = int(agree[0].item())  # exact: a round count is far below 2^24
+            send, recv, so, ro = [], [], 0, 0
+            for p in range(W):
+                send.append((so, int(in_bytes[p])))
+                recv.append((ro, int(out_bytes[p])))
+                so += int(in_bytes[p])
+                ro += int(out_bytes[p])
+            self._exchange(inp.data_ptr(), out.data_ptr(), send, recv, stream, rounds=rounds)
 
     def reduce_scatter_(self, out: torch.Tensor, inp: torch.Tensor, op: int = _native.OP_SUM, scale: float = 1.0,
                         stream: Optional[torch.cuda.Stream] = None) -> None:
