@@ -9,16 +9,15 @@ gradient byte through NCCL (manager.py:466-468), this group
 * runs every collective as ONE hand-written sm_100a kernel over NVLink peer memory (P2P loads +
   stores, epoch-tagged flags, bounded abortable spins) on a dedicated comm stream: all-reduce
   (one-/two-shot, NVLS) with the 1/N scale, dtype handling and the non-participant zero
-  contribution fused; all-gather, broadcast and equal-split all-to-all as a push exchange through
-  staging slots; reduce-scatter; send / recv through per-pair mailboxes -- each moving exactly the
+  contribution fused; all-gather, broadcast and all-to-all (equal or per-peer splits) as a push exchange
+  through staging slots; reduce-scatter; send / recv through per-pair mailboxes -- each moving exactly the
   algorithmic bytes (``csrc/kernels/{allreduce,allreduce_nvls,collectives,quant,zero1}.cu``);
 * surfaces peer death as a latched ``errored()`` (kernel spin timeout / abort
   flag), the in-kernel analogue of ``ncclCommAbort``;
 * exposes ``alloc_symmetric`` so gradient buckets can live in peer-visible memory
   and be reduced with zero copies.
 
-What the kernels cannot express (CPU tensors, non-contiguous views, integer reductions, all-to-all
-with unequal splits) goes to a lazily created NCCL *sidecar* group over the same store, so the
+What the kernels cannot express (CPU tensors, non-contiguous views, integer reductions) goes to a lazily created NCCL *sidecar* group over the same store, so the
 full c10d surface keeps working; nothing on the training or heal paths uses it.
 """
 
@@ -277,7 +276,7 @@ class ProcessGroupB200(ProcessGroup):
 
     # Everything below is ONE push-exchange / reduce-scatter / p2p kernel per tensor (csrc/kernels/collectives.cu):
     # algorithmic bytes over NVLink, no zero-padded all-reduce emulation, no NCCL. Only what the kernels cannot
-    # express (CPU tensors, non-contiguous views, integer reductions, unequal all-to-all splits) goes to the sidecar.
+    # express (CPU tensors, non-contiguous views, integer reductions) goes to the sidecar.
     @staticmethod
     def _raw_ok(t: torch.Tensor) -> bool:
         return t.is_cuda and t.is_contiguous()
