@@ -35,6 +35,7 @@ def worker(a: argparse.Namespace) -> None:
     from torch.distributed.fsdp import fully_shard
 
     from torchft_b200 import ManagedProcessGroup, Manager, Optimizer, ProcessGroupB200
+    from torchft_b200.parallel.hsdp import fsdp_local_state, load_fsdp_local_state
 
     group = int(os.environ["REPLICA_GROUP_ID"])
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -53,7 +54,8 @@ def worker(a: argparse.Namespace) -> None:
     pg = ProcessGroupB200(timeout=timedelta(seconds=30))
     manager = Manager(pg=pg, min_replica_size=a.groups, load_state_dict=None, state_dict=None, replica_id=f"hsdp_{group}",
                       timeout=timedelta(seconds=30), quorum_timeout=timedelta(seconds=60), init_sync=False)
-    manager.register_state_dict_fn("noop", lambda sd: None, lambda: {})
+    # heal: rank i of a (re)joining group pulls rank i's parameter / optimizer shards of a healthy group, in place
+    manager.register_state_dict_fn("hsdp", lambda sd: load_fsdp_local_state(model, inner, sd), lambda: fsdp_local_state(model, inner))
     replicate_pg = ManagedProcessGroup(manager)
 
     def cross_replica_hook(shard_grad: torch.Tensor) -> None:

@@ -16,11 +16,64 @@ from __future__ import annotations
 
 import os
 from datetime import timedelta
-from typing import Any, Optional
+from typing import Any, Dict, Optional
 
 import torch
 import torch.distributed as dist
 from torch.distributed import TCPStore
+
+
+def _local(t: Any) -> Any:
+    """The local shard of a DTensor (aliasing its storage), anything else unchanged."""
+    return t.to_local() if hasattr(t, "to_local") else t
+
+
+def fsdp_local_state(model: torch.nn.Module, optim: torch.optim.Optimizer) -> Dict[str, Any]:
+    """Heal payload of ONE rank of an FSDP2-sharded model: its local parameter shards and its local optimizer-state
+    shards, keyed by parameter name, as plain tensors that ALIAS the live storage. A healthy replica serves them to the
+    same group rank of the healing replica group (the reference heals rank i from rank i: manager.py:700-716); an
+    in-place transport (``P2PTransport``) on the healing side writes straight into the tensors this function returns
+    there, so a heal is one ranged NVLink copy per shard and no re-sharding is involved (same shard layout on both sides:
+    replica groups are congruent by construction)."""
+    params, state = {}, {}
+    for name, p in model.named_parameters():
+        params[name] = _local(p.detach())
+        st = optim.state.get(p)
+        if st:
+            state[name] = {k: _local(v.detach()) if isinstance(v, torch.Tensor) else v for k, v in st.items()}
+    return {"params": params, "optim": state}
+
+
+@torch.no_grad()
+def load_fsdp_local_state(model: torch.nn.Module, optim: torch.optim.Optimizer, payload: Dict[str, Any]) -> None:
+    """Install a payload of :func:`fsdp_local_state` (tensors that are already the live storage are left alone;
+    optimizer state a fresh replica does not have yet is created with the parameter's own sharding)."""
+    for name, p in model.named_parameters():
+        src = payload["params"][name]
+        dst = _local(p.detach())
+        if src.shape != dst.shape:
+            raise ValueError(f"shard of {name}: got {tuple(src.shape)}, this rank holds {tuple(dst.shape)} (different sharding?)")
+        if src.data_ptr() != dst.data_ptr():
+            dst.copy_(src)
+        incoming = payload["optim"].get(name)
+        if incoming is None:
+            optim.state.pop(p, None)  # the source had not stepped this parameter yet
+            continue
+        st = optim.state[p]  # defaultdict: creates the entry on a fresh replica
+        for k, v in incoming.items():
+            if not isinstance(v, torch.Tensor):
+                st[k] = v
+                continue
+            cur = st.get(k)
+            if cur is None:
+                if v.dim() > 0 and v.shape == dst.shape:
+                    cur = torch.zeros_like(p, dtype=v.dtype)  # per-element state follows the parameter's sharding
+                else:
+                    cur = v.detach().clone()                  # scalars (AdamW's step counter) are plain tensors
+                st[k] = cur
+            tgt = _local(cur)
+            if tgt.data_ptr() != v.data_ptr():
+                tgt.copy_(v)
 
 
 class SymmetricShardGrads:
@@ -130,7 +183,9 @@ class HSDPTrainer:
                                timeout=timeout, quorum_timeout=timeout, connect_timeout=timeout, rank=self.group_rank,
                                world_size=shards, store_addr="127.0.0.1", store_port=int(port[0]),
                                lighthouse_addr=lighthouse_addr, replica_id=f"{replica_prefix}_{self.group}", init_sync=False)
-        self.manager.register_state_dict_fn("model", lambda sd: None, lambda: {})
+        # heal: rank i of a joining group pulls the parameter and optimizer shards of rank i of a healthy group in place
+        self.manager.register_state_dict_fn("hsdp", lambda sd: load_fsdp_local_state(self.model, self.inner, sd),
+                                            lambda: fsdp_local_state(self.model, self.inner))
         replicate = ManagedProcessGroup(self.manager)
 
         def cross_replica(shard_grad: torch.Tensor) -> None:
