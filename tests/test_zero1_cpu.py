@@ -282,3 +282,82 @@ def test_liveness_watch_aborts_the_group_when_a_quorum_member_stops_heartbeating
         for m in managers:
             m.shutdown(wait=False)
         lh.shutdown()
+
+
+# ----------------------------------------------------------------------------- randomized protocol walk
+@pytest.mark.parametrize("seed", range(6))
+def test_random_walk_of_kills_rejoins_and_split_commits_keeps_holders_consistent(seed):
+    """Long random sequences of membership changes (several replicas may die or rejoin in one transition), committed
+    steps and split commits, for k in {1, 2, 3}. Checked after every event against an independent bitmap oracle:
+    (1) every holder of an element carries the same value (holders are bit-identical replicas of a slice);
+    (2) an element is counted lost exactly when no surviving up-to-date replica held it -- never otherwise; in particular
+        never while every replica is alive and none missed a commit (after a split commit the slices whose holders all
+        missed the update ARE re-seeded: stale state is never mixed with current state);
+    (3) elements that were never lost equal the number of committed updates."""
+    rng = np.random.default_rng(1000 + seed)
+    n, k = 8, int(rng.integers(1, 4))
+    sim = _Sim(n, k)
+    sim.configure(range(n))
+    ever_lost = np.zeros(NUMEL, dtype=bool)
+    alive = set(range(n))
+
+    def reconfigure(members):
+        members = sorted(members)
+        tmax = max(sim.t[m] for m in members)
+        available = np.zeros(NUMEL, dtype=bool)  # oracle: somebody up to date in the new quorum holds it
+        for m in members:
+            if sim.t[m] == tmax:
+                available |= _mask(sim.hold[m], NUMEL)
+        before = sim.lost
+        stale = any(sim.t[m] != tmax for m in members)
+        sim.configure(members)
+        world = len(members)
+        expect_lost = 0
+        for i, m in enumerate(members):
+            need = _mask(sim.L.held(i, world), NUMEL)
+            gone = need & ~available
+            expect_lost += int(gone.sum())
+            ever_lost[gone] = True
+        assert sim.lost - before == expect_lost
+        if len(alive) == n and not stale and expect_lost:
+            raise AssertionError("state lost although every replica is alive and up to date")
+
+    def check():
+        members, world = sim.members, len(sim.members)
+        tmax = max(sim.t[m] for m in members)
+        value = np.full(NUMEL, np.nan)
+        for i, m in enumerate(members):
+            if sim.t[m] != tmax:
+                continue
+            for lo, hi in sim.L.held(i, world):
+                seg, cur = sim.state[m][lo:hi], value[lo:hi]
+                fresh = np.isnan(cur)
+                assert (seg[~fresh] == cur[~fresh]).all(), "holders of one slice disagree"
+                cur[fresh] = seg[fresh]
+        ok = ~ever_lost & ~np.isnan(value)
+        assert (value[ok] == tmax).all()
+        assert not np.isnan(value).any(), "an element has no up-to-date holder inside the quorum"
+
+    for _ in range(120):
+        ev = rng.random()
+        if ev < 0.45:
+            sim.step()
+        elif ev < 0.55 and len(sim.members) > 1:
+            # split commit: a random non-empty strict subset applies the update, then everybody meets in a new quorum
+            sub = [m for m in sim.members if rng.random() < 0.6] or [sim.members[0]]
+            sim.step(commit_on=sub)
+            reconfigure(sim.members)
+        elif ev < 0.8 and len(alive) > 1:
+            for m in rng.choice(sorted(alive), size=int(rng.integers(1, min(3, len(alive)))), replace=False):
+                alive.discard(int(m))
+            reconfigure(alive)
+        else:
+            dead = sorted(set(range(n)) - alive)
+            for m in dead[: int(rng.integers(1, 3))]:
+                sim.state[m] = np.zeros(NUMEL)  # restarted process: seed state, step 0
+                sim.hold[m] = [(0, NUMEL)]
+                sim.t[m] = 0
+                alive.add(m)
+            if dead:
+                reconfigure(alive)
+        check()
