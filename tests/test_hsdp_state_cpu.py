@@ -16,10 +16,19 @@ from torchft_b200.parallel.hsdp import fsdp_local_state, load_fsdp_local_state
 def gloo_world():
     if dist.is_initialized():
         pytest.skip("a default process group already exists in this interpreter")
+    keys = ("MASTER_ADDR", "MASTER_PORT", "RANK", "WORLD_SIZE")
+    saved = {k: os.environ.get(k) for k in keys}
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29917", RANK="0", WORLD_SIZE="1")
     dist.init_process_group("gloo")
-    yield
-    dist.destroy_process_group()
+    try:
+        yield
+    finally:
+        dist.destroy_process_group()
+        for k, v in saved.items():  # later tests spawn torchrun workers: do not leak a rendezvous into their environment
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def _replica(seed: int):
