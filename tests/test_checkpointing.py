@@ -325,3 +325,72 @@ def test_p2p_clean_session_roundtrip_of_small_objects():
     finally:
         src.shutdown(wait=False)
         dst.shutdown(wait=False)
+
+
+# ----------------------------------------------------------------------------- defaults that must work across hosts
+def test_default_heal_transport_is_p2p_only_for_single_host_groups(monkeypatch):
+    """CUDA-IPC handles open only on the exporting host: the NVLink transport may be the default only when the process
+    group itself is confined to one host; any other group gets the HTTP transport like the reference's default
+    (manager.py:277-281). Round-1 advisor finding: P2P was picked whenever CUDA was available."""
+    from types import SimpleNamespace
+
+    import torch
+
+    from torchft_b200.checkpointing import http_transport, p2p_transport
+    from torchft_b200.manager import Manager
+
+    made = []
+    monkeypatch.setattr(p2p_transport, "P2PTransport", lambda **kw: made.append("p2p") or "P2P")
+    monkeypatch.setattr(http_transport, "HTTPTransport", lambda **kw: made.append("http") or "HTTP")
+
+    def pick(pg, cuda, env=None):
+        monkeypatch.setattr(torch.cuda, "is_available", lambda: cuda)
+        if env is None:
+            monkeypatch.delenv("TORCHFT_B200_TRANSPORT", raising=False)
+        else:
+            monkeypatch.setenv("TORCHFT_B200_TRANSPORT", env)
+        m = SimpleNamespace(_pg=pg, _timeout=timedelta(seconds=5), _heal_targets=lambda: {})
+        return Manager._default_transport(m)
+
+    assert pick(SimpleNamespace(single_host=True), cuda=True) == "P2P"
+    assert pick(SimpleNamespace(single_host=True), cuda=False) == "HTTP"      # no GPU: nothing to pull over NVLink
+    assert pick(SimpleNamespace(), cuda=True) == "HTTP"                        # ProcessGroupNCCL / Gloo: may span hosts
+    assert pick(SimpleNamespace(single_host="yes"), cuda=True) == "HTTP"       # only a literal True counts
+    assert pick(SimpleNamespace(), cuda=True, env="p2p") == "P2P"              # explicit override
+    assert pick(SimpleNamespace(single_host=True), cuda=True, env="http") == "HTTP"
+
+
+def test_advertise_host_prefers_env_then_hostname_then_routable_interface(monkeypatch):
+    import socket
+
+    from torchft_b200.checkpointing.transport import advertise_host
+
+    monkeypatch.setenv("TORCHFT_ADVERTISE_HOST", "10.1.2.3")
+    assert advertise_host() == "10.1.2.3"
+    monkeypatch.delenv("TORCHFT_ADVERTISE_HOST")
+    monkeypatch.setattr(socket, "gethostname", lambda: "node-17")
+    monkeypatch.setattr(socket, "getaddrinfo", lambda h, p: [("ok",)])
+    assert advertise_host() == "node-17"
+
+    def unresolvable(h, p):
+        raise OSError("name or service not known")
+
+    class _Sock:
+        def __init__(self, *a):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def connect(self, addr):
+            pass
+
+        def getsockname(self):
+            return ("192.168.7.9", 5555)
+
+    monkeypatch.setattr(socket, "getaddrinfo", unresolvable)
+    monkeypatch.setattr(socket, "socket", _Sock)
+    assert advertise_host() == "192.168.7.9"  # never silently loopback when an off-host interface exists
