@@ -357,6 +357,36 @@ def test_p2p_transport_inplace_targets_matched_by_key_path(K):
         dst.shutdown()
 
 
+def test_p2p_transport_moves_host_tensors_through_the_gpu_not_through_the_manifest(K):
+    """CPU leaves of the source's state (DiLoCo's backup weights with ``backup_device=None``) are staged on the GPU and
+    pulled by the same copy kernel; the manifest stays small, and they come back as CPU tensors -- in place when the
+    receiver offers a matching CPU target. Round-1 advisor finding: they used to be hex-pickled into the manifest."""
+    from datetime import timedelta
+
+    from torchft_b200.checkpointing import P2PTransport
+
+    torch.manual_seed(10)
+    backup_src, other_src = torch.randn(300_000), torch.randn(5_000, dtype=torch.float64)  # 1.2 MB and 40 KB on the host
+    w_src = torch.randn(1000, device="cuda")
+    sender_sd = {"w": w_src, "backup": backup_src, "other": other_src, "tiny": torch.tensor([1.0, 2.0]), "n": 3}
+    backup_dst = torch.zeros(300_000)
+    fresh_sd = {"w": torch.zeros(1000, device="cuda"), "backup": backup_dst}
+    t = timedelta(seconds=10)
+    src, dst = P2PTransport(t), P2PTransport(t, state_dict=lambda: fresh_sd)
+    try:
+        src.send_checkpoint([1], 5, sender_sd, t)
+        assert len(src._manifest) < 64 << 10, "host tensors must not be embedded in the manifest"
+        got = dst.recv_checkpoint(0, src.metadata(), 5, t)
+        torch.cuda.synchronize()
+        assert got["backup"] is backup_dst and torch.equal(backup_dst, backup_src)          # in place, on the host
+        assert not got["other"].is_cuda and got["other"].dtype == torch.float64 and torch.equal(got["other"], other_src)
+        assert torch.equal(got["tiny"], torch.tensor([1.0, 2.0])) and got["n"] == 3 and torch.equal(got["w"], w_src)
+        src.disallow_checkpoint()
+    finally:
+        src.shutdown()
+        dst.shutdown()
+
+
 def _rms(x, g, eps):
     return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * g
 
