@@ -83,6 +83,7 @@ class Heartbeats:
 
 
 def ask_all(clients, ids, step):
+    ids = list(ids)
     """All replicas in ``ids`` request a quorum at once; returns (ms until the last one was answered, sizes)."""
     barrier = threading.Barrier(len(ids) + 1)
     done = {}
@@ -90,14 +91,16 @@ def ask_all(clients, ids, step):
     def run(i: int) -> None:
         barrier.wait()
         q = clients[i].quorum(replica_id=f"r{i}", timeout=T, address=f"http://a{i}", store_address=f"s{i}:1", step=step, world_size=1)
-        done[i] = (time.perf_counter(), len(q.participants))
+        # stamp first; touch the result (a pybind conversion of all N members under the GIL: with N client threads in ONE
+        # process that alone cost 100+ ms at N = 64 and was mistaken for server time) only for one replica
+        done[i] = (time.perf_counter(), len(q.participants) if i == ids[0] else None)
 
     ts = [threading.Thread(target=run, args=(i,)) for i in ids]
     [t.start() for t in ts]
     barrier.wait()
     t0 = time.perf_counter()
     [t.join() for t in ts]
-    return (max(v[0] for v in done.values()) - t0) * 1e3, sorted({v[1] for v in done.values()})
+    return (max(v[0] for v in done.values()) - t0) * 1e3, sorted({v[1] for v in done.values() if v[1] is not None})
 
 
 def bench_quorum_formation(n: int, rounds: int) -> dict:
@@ -138,7 +141,7 @@ def main() -> None:
     a = ap.parse_args()
     res = {"host_cpus": os.cpu_count()}
     res.update(bench_manager_rpcs(a.iters))
-    res["quorum_formation"] = [bench_quorum_formation(n, 5) for n in (2, 8, 32, 64)]
+    res["quorum_formation"] = [bench_quorum_formation(n, 5) for n in (2, 8, 32, 64, 128, 256, 512)]
     res["shrink_after_failure"] = [bench_shrink(n) for n in (2, 8)]
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     with open(a.out, "w") as f:

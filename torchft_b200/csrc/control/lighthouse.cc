@@ -79,7 +79,16 @@ void Lighthouse::tick_locked() {
   q.created_ms = unix_ms();
   state_.prev_quorum = q;
   state_.participants.clear();
-  history_.emplace_back(++gen_, std::move(q));
+  Formed f;
+  f.gen = ++gen_;
+  {
+    Writer w;
+    q.encode(w);
+    f.wire = std::make_shared<const std::string>(w.take());
+  }
+  for (const auto& p : q.participants) f.members.insert(p.replica_id);
+  f.quorum = std::move(q);
+  history_.push_back(std::move(f));
   while (history_.size() > 64) history_.pop_front();
   cv_.notify_all();
 }
@@ -106,19 +115,34 @@ uint32_t Lighthouse::handle_rpc(uint32_t method, const std::string& req, TimePoi
   state_.heartbeats[requester.replica_id] = now;  // a quorum request is an implicit heartbeat
   state_.participants[requester.replica_id] = ParticipantDetails{now, requester};
   uint64_t seen = gen_;  // subscribe BEFORE the eager tick so its quorum is not missed
-  tick_locked();
+  // Eager tick (reference: every request ticks, lighthouse.rs:292-343) -- but only when this request can have completed a
+  // quorum. Without the join timeout (which the periodic tick serves) a quorum needs every member of the previous quorum
+  // (fast path) or every healthy replica among the participants, so fewer participants than both cannot decide anything.
+  // quorum_compute sorts and formats over all replicas: running it for each of N simultaneous joiners made forming a
+  // quorum O(N^2 log N) under the global lock (512 replica groups: 340 ms; with the counting pre-check below: see
+  // profiles/control_plane_bench_r2.json).
+  bool may_decide = true;
+  {
+    const size_t np = state_.participants.size();
+    const size_t prev = state_.prev_quorum.has_value() ? state_.prev_quorum->participants.size() : (size_t)-1;
+    if (np < prev) {
+      size_t healthy = 0;
+      for (const auto& hb : state_.heartbeats)
+        if (now - hb.second < (int64_t)opt_.heartbeat_timeout_ms) ++healthy;
+      may_decide = np >= healthy;
+    }
+  }
+  if (may_decide) tick_locked();
   while (true) {
     // replay every quorum formed since we subscribed, oldest first
-    for (const auto& [g, q] : history_) {
-      if (g <= seen) continue;
-      seen = g;
-      for (const auto& p : q.participants) {
-        if (p.replica_id == requester.replica_id) {
-          Writer w;
-          q.encode(w);
-          *resp = w.take();
-          return kStatusOk;
-        }
+    for (const auto& f : history_) {
+      if (f.gen <= seen) continue;
+      seen = f.gen;
+      if (f.members.count(requester.replica_id)) {
+        std::shared_ptr<const std::string> wire = f.wire;
+        lk.unlock();  // copy the (shared, immutable) encoding outside the lock
+        *resp = *wire;
+        return kStatusOk;
       }
       // formed without us (e.g. shrink_only round): rejoin the next round
       state_.participants[requester.replica_id] = ParticipantDetails{monotonic_ms(), requester};

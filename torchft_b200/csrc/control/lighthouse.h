@@ -4,6 +4,7 @@
 #include <condition_variable>
 #include <deque>
 #include <memory>
+#include <set>
 #include <mutex>
 #include <thread>
 
@@ -36,7 +37,15 @@ class Lighthouse : public RpcServer {
   LighthouseState state_;
   // every formed quorum gets a generation number; waiters replay the ones they missed
   uint64_t gen_ = 0;
-  std::deque<std::pair<uint64_t, Quorum>> history_;
+  // (generation, quorum, its wire encoding, member ids): encoded ONCE when the quorum forms; every waiter of a large
+  // quorum used to re-encode all N members under the lock (O(N^2) bytes per round)
+  struct Formed {
+    uint64_t gen;
+    Quorum quorum;
+    std::shared_ptr<const std::string> wire;
+    std::set<std::string> members;
+  };
+  std::deque<Formed> history_;
   std::string last_reason_;
   std::thread tick_thread_;
   bool shutdown_ = false;
