@@ -156,6 +156,45 @@ def test_torchx_component_spec_and_import_gate():
             tx.hsdp(replicas=2)
 
 
+def test_torchx_component_builds_an_appdef_against_the_torchx_specs_api(monkeypatch):
+    """torchx is not in this image: run the component against a stand-in ``torchx.specs`` with the real constructors'
+    keyword names (specs.resource / Role / AppDef, reference torchft/torchx.py:60-89) so the conversion code executes."""
+    import sys
+    import types
+
+    from torchft_b200 import torchx as tx
+
+    specs = types.ModuleType("torchx.specs")
+
+    class _Rec:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    class Role(_Rec):
+        pass
+
+    class AppDef(_Rec):
+        pass
+
+    specs.Role, specs.AppDef = Role, AppDef
+    specs.resource = lambda cpu, gpu, memMB, h=None: ("res", cpu, gpu, memMB, h)
+    pkg = types.ModuleType("torchx")
+    pkg.specs = specs
+    monkeypatch.setitem(sys.modules, "torchx", pkg)
+    monkeypatch.setitem(sys.modules, "torchx.specs", specs)
+    monkeypatch.setenv("TORCHFT_LIGHTHOUSE", "http://lh:29510")
+    app = tx.hsdp("--steps", "7", replicas=2, workers_per_replica=4, max_restarts=3, script="train.py", image="img:1",
+                  env={"FOO": "bar"}, gpu=4, cpu=16, memMB=4096)
+    assert isinstance(app, AppDef) and app.name == "torchft_b200" and len(app.roles) == 2
+    r1 = app.roles[1]
+    assert isinstance(r1, Role) and r1.name == "replica_group_1" and r1.image == "img:1" and r1.max_retries == 0  # restarts are torchrun's job
+    assert r1.num_replicas == 1 and r1.min_replicas == 1 and r1.resource == ("res", 16, 4, 4096, None)
+    assert r1.env["REPLICA_GROUP_ID"] == "1" and r1.env["NUM_REPLICA_GROUPS"] == "2" and r1.env["FOO"] == "bar"
+    assert r1.env["TORCHFT_LIGHTHOUSE"] == "http://lh:29510"
+    assert "--nproc_per_node=4" in " ".join(r1.args).replace("--nproc-per-node", "--nproc_per_node") and r1.args[-3:] == ["train.py", "--steps", "7"]
+    assert "--master_port=29601" in r1.args and any(a.replace("-", "_") == "__max_restarts=3" for a in r1.args)
+
+
 def test_failure_injector_comms_and_stall():
     pg = FakeProcessGroupWrapper(ProcessGroupDummy(0, 1))
     aborted = []

@@ -33,8 +33,8 @@ def hsdp(*script_args: str, replicas: int = 2, workers_per_replica: int = 1, max
     roles: List[Role] = hsdp_spec(*script_args, replicas=replicas, workers_per_replica=workers_per_replica,
                                  max_restarts=max_restarts, script=script, env=env,
                                  lighthouse=os.environ.get("TORCHFT_LIGHTHOUSE"))
-    resource = specs.resource(cpu=cpu, gpu=gpu, memMB=memMB, h=h)  # pragma: no cover
-    return specs.AppDef(  # pragma: no cover
+    resource = specs.resource(cpu=cpu, gpu=gpu, memMB=memMB, h=h)
+    return specs.AppDef(
         name="torchft_b200",
         roles=[specs.Role(name=r.name, image=image, min_replicas=1, num_replicas=1, entrypoint=r.entrypoint,
                           args=r.args, env=r.env, max_retries=r.max_retries, resource=resource) for r in roles])
